@@ -1,0 +1,712 @@
+// track2d_reset.cu -- Track1v1Env.reset (envs/track_1v1.py:134-168): a fresh random map per episode
+// (init_maze, :218-240), spawn sampling (generators.py:21-94), scripted-target reset, counters, and the
+// first observation.  One WARP per env being reset; the map is built as a bit grid in shared memory
+// and written to HBM with coalesced 4-byte stores.
+//
+// Two RNG back-ends (track2d.h):
+//   T2D_RNG_PHILOX  warp-parallel sampling with the reference's distributions:
+//                   k = int(0.15*u*6400) distinct obstacles by parallel draw-until-new with warp match /
+//                   ballot de-duplication (== sequential sampling without replacement), spawn = j-th free
+//                   cell by popcount prefix scan, target = uniform free cell of the 2x2 block.
+//   T2D_RNG_NUMPY   lane 0 replays numpy's legacy RandomState calls in the reference's exact order
+//                   (random_sample, permutation(6400)[:k], permutation(n_free)[:2], ...), so env e equals
+//                   the reference after np.random.seed(seed + e) bit for bit.  Slow by construction (four
+//                   sequential Fisher-Yates shuffles of ~6400 per reset); it is the parity mode.
+#include "track2d_common.cuh"
+#include "track2d_nav.cuh"
+
+namespace {
+
+// ---- shared helpers -------------------------------------------------------------------------------
+
+// bit grid with the 6-cell wall frame; interior (map rows/cols 1..H-2) cleared
+__device__ void bm_init(uint32_t *bm, int H, int W, int lane) {
+    const int lastc = W - 2 + T2D_PAD; // last interior padded column
+    for (int i = lane; i < T2D_MAP_WORDS; i += 32) {
+        int pr = i / 3, wi = i - 3 * pr;
+        uint32_t v = 0xFFFFFFFFu;
+        if (pr >= T2D_PAD + 1 && pr <= H - 2 + T2D_PAD) {
+            int lo = max(T2D_PAD + 1, 32 * wi), hi = min(lastc, 32 * wi + 31); // zero [lo, hi]
+            if (lo <= hi) {
+                uint32_t span = hi - lo + 1;
+                uint32_t zmask = (span == 32 ? 0xFFFFFFFFu : ((1u << span) - 1u)) << (lo - 32 * wi);
+                v = ~zmask;
+            }
+        }
+        bm[i] = v;
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ int bm_wall(const uint32_t *bm, int r, int c) { return (bm[map_word_index(r, c)] >> ((c + T2D_PAD) & 31)) & 1u; }
+__device__ __forceinline__ void bm_set(uint32_t *bm, int r, int c) { atomicOr(&bm[map_word_index(r, c)], map_bit_of(c)); }
+__device__ __forceinline__ void bm_clear(uint32_t *bm, int r, int c) { atomicAnd(&bm[map_word_index(r, c)], ~map_bit_of(c)); }
+
+// generators.py:115-145 RandomMazeGenerator._generate_maze, sequential (one thread), any RNG
+template <typename Rng>
+__device__ void maze_walk(uint32_t *bm, Rng &rng, double r) {
+    const int sh = 81;
+    int complexity = (int)(r * (double)(5 * (sh + sh)));
+    int density = (int)(r * (double)((sh / 2) * (sh / 2)));
+    for (int i = 0; i < density; i++) {
+        int x = (int)rng.interval(sh / 2) * 2; // randint(0, 41) * 2, x before y
+        int y = (int)rng.interval(sh / 2) * 2;
+        bm[map_word_index(y, x)] |= map_bit_of(x);
+        for (int j = 0; j < complexity; j++) {
+            int ny[4], nx[4], nn = 0;
+            if (x > 1) { ny[nn] = y; nx[nn] = x - 2; nn++; }
+            if (x < sh - 2) { ny[nn] = y; nx[nn] = x + 2; nn++; }
+            if (y > 1) { ny[nn] = y - 2; nx[nn] = x; nn++; }
+            if (y < sh - 2) { ny[nn] = y + 2; nx[nn] = x; nn++; }
+            int pick = (int)rng.interval((uint32_t)(nn - 1));
+            int y_ = ny[0], x_ = nx[0];
+#pragma unroll
+            for (int q = 1; q < 4; q++)
+                if (pick == q) { y_ = ny[q]; x_ = nx[q]; }
+            if (!bm_wall(bm, y_, x_)) {
+                bm[map_word_index(y_, x_)] |= map_bit_of(x_);
+                int my = y_ + (y - y_) / 2, mx = x_ + (x - x_) / 2;
+                bm[map_word_index(my, mx)] |= map_bit_of(mx);
+                x = x_;
+                y = y_;
+            }
+        }
+    }
+}
+
+// number of free cells, and the j-th free cell in row-major order (np.where(maze == 0) order).
+// Each lane owns 9 consecutive words of the grid.
+__device__ int bm_count_free(const uint32_t *bm, int lane) {
+    int n = 0;
+#pragma unroll
+    for (int i = 0; i < 9; i++) n += __popc(~bm[9 * lane + i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xFFFFFFFFu, n, o);
+    return n;
+}
+__device__ uint32_t bm_select_free(const uint32_t *bm, int j, int lane) { // returns row | col << 8
+    int mine = 0;
+#pragma unroll
+    for (int i = 0; i < 9; i++) mine += __popc(~bm[9 * lane + i]);
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    int excl = incl - mine;
+    uint32_t found = 0;
+    if (j >= excl && j < incl) {
+        int rem = j - excl;
+        for (int i = 0; i < 9; i++) {
+            uint32_t z = ~bm[9 * lane + i];
+            int pc = __popc(z);
+            if (rem < pc) {
+                int bit = __fns(z, 0, rem + 1);
+                int word = 9 * lane + i;
+                int pr = word / 3, pcol = 32 * (word - 3 * pr) + bit;
+                found = (uint32_t)(pr - T2D_PAD) | ((uint32_t)(pcol - T2D_PAD) << 8);
+                break;
+            }
+            rem -= pc;
+        }
+    }
+    uint32_t owner = __ballot_sync(0xFFFFFFFFu, j >= excl && j < incl);
+    return __shfl_sync(0xFFFFFFFFu, found, __ffs(owner) - 1);
+}
+
+// generators.py:82-94 get_around(state, 1): free cells of {r-1, r} x {c-1, c} in row-major order
+__device__ __forceinline__ int around_free(const uint32_t *bm, int r, int c, int cr[4], int cc[4]) {
+    int n = 0;
+    for (int rr = max(0, r - 1); rr < r + 1; rr++)
+        for (int q = max(0, c - 1); q < c + 1; q++)
+            if (!bm_wall(bm, rr, q)) { cr[n] = rr; cc[n] = q; n++; }
+    return n;
+}
+
+template <typename ObsT>
+__device__ void write_partial_obs(const uint32_t *bm, uint32_t p, ObsT *__restrict__ o, int lane) {
+    int r0 = p & 255, c0 = (p >> 8) & 255, r1 = (p >> 16) & 255, c1 = p >> 24;
+    for (int i = lane; i < T2D_ENV_CELLS; i += 32) {
+        int a = i >= T2D_WIN_CELLS;
+        int cell = i - T2D_WIN_CELLS * a;
+        int wr = cell / T2D_WIN, wc = cell - T2D_WIN * wr;
+        int r = (a ? r1 : r0) - T2D_PAD + wr, c = (a ? c1 : c0) - T2D_PAD + wc;
+        int v = (bm[(r + T2D_PAD) * T2D_ROW_WORDS + ((c + T2D_PAD) >> 5)] >> ((c + T2D_PAD) & 31)) & 1u;
+        if (r == r0 && c == c0) v = 2;
+        if (r == r1 && c == c1) v = 4;
+        if (cell == 84) v = 2 + 2 * a;
+        o[i] = (ObsT)v;
+    }
+}
+
+// ---- numpy legacy sampling helpers (T2D_RNG_NUMPY) ------------------------------------------------------
+// perm / freel (numpy sampling) and the A* maps are never live at the same time: one union.
+struct NumpyScratch {
+    uint32_t key[T2D_MT_N];
+    uint32_t bm[T2D_MAP_WORDS];
+    union {
+        struct {
+            uint16_t perm[82 * 82];
+            uint16_t freel[82 * 82];
+        };
+        AStarScratch astar;
+    };
+};
+struct PhiloxNavScratch {
+    uint32_t bm[T2D_MAP_WORDS];
+    AStarScratch astar;
+};
+
+// np.random.permutation(n) into s.perm: arange by the warp, legacy shuffle by lane 0
+__device__ void np_permutation(NumpyScratch &s, MtRng &rng, int n, int lane) {
+    for (int i = lane; i < n; i += 32) s.perm[i] = (uint16_t)i;
+    __syncwarp();
+    if (lane == 0) {
+        for (int i = n - 1; i >= 1; i--) {
+            int j = (int)rng.interval((uint32_t)i);
+            uint16_t t = s.perm[i];
+            s.perm[i] = s.perm[j];
+            s.perm[j] = t;
+        }
+    }
+    __syncwarp();
+}
+
+// np.where(maze == 0) row-major over the H x W map -> s.freel (cell = r * W + c); returns the count
+__device__ int np_free_list(NumpyScratch &s, int H, int W, int lane) {
+    int base = 0;
+    const int cells = H * W;
+    for (int i0 = 0; i0 < cells; i0 += 32) {
+        int i = i0 + lane;
+        bool fr = false;
+        if (i < cells) {
+            int r = i / W, c = i - r * W;
+            fr = !bm_wall(s.bm, r, c);
+        }
+        uint32_t msk = __ballot_sync(0xFFFFFFFFu, fr);
+        if (fr) s.freel[base + __popc(msk & ((1u << lane) - 1u))] = (uint16_t)i;
+        base += __popc(msk);
+    }
+    __syncwarp();
+    return base;
+}
+
+// RPF: advance the static-goal cursor (generators.py:47-50) and return that corner
+__device__ __forceinline__ uint32_t rpf_next_goal(const World &w, int e, int lane) {
+    uint32_t word = w.rpf[e];
+    uint32_t v = ((word & 255u) + 1u) & 3u;
+    __syncwarp();
+    if (lane == 0) w.rpf[e] = (word & ~255u) | v;
+    __syncwarp();
+    return rpf_corner(w.H, w.W, (int)v);
+}
+
+// generators.py:38-51 sample_goal(num <= 2) on the generator maze (non-static) or the RPF corner cursor
+__device__ void np_sample_goal(const World &w, NumpyScratch &s, MtRng &rng, int e, int num, uint32_t g[2], int lane) {
+    if (w.target_mode != T2D_TARGET_RPF) {
+        int n = np_free_list(s, w.H, w.W, lane);
+        np_permutation(s, rng, n, lane);
+        for (int i = 0; i < num; i++) {
+            int cell = s.freel[s.perm[i]];
+            g[i] = (uint32_t)(cell / w.W) | ((uint32_t)(cell % w.W) << 8);
+        }
+        __syncwarp();
+    } else {
+        uint32_t corner = rpf_next_goal(w, e, lane);
+        for (int i = 0; i < num; i++) g[i] = corner;
+    }
+}
+
+// static_goals (generators.py:12-19) on a generator-maze copy: remember which corners were walls in the
+// ENV map (Track1v1Env.maze is copied before static_goals runs, track_1v1.py:234-236), clear them.
+__device__ __forceinline__ uint32_t rpf_clear_corners(uint32_t *bm, int H, int W, int lane) {
+    uint32_t wallbits = 0;
+    for (int q = 0; q < 4; q++) {
+        uint32_t cn = rpf_corner(H, W, q);
+        wallbits |= (uint32_t)bm_wall(bm, cn & 255, cn >> 8) << q;
+    }
+    __syncwarp();
+    if (lane == 0)
+        for (int q = 0; q < 4; q++) {
+            uint32_t cn = rpf_corner(H, W, q);
+            bm[map_word_index(cn & 255, cn >> 8)] &= ~map_bit_of(cn >> 8);
+        }
+    __syncwarp();
+    return wallbits;
+}
+
+// ---- Navigator glue (envs/navigator.py) -------------------------------------------------------------
+struct NumpyNavPolicy {
+    const World &w; int e; NumpyScratch &s; MtRng &rng;
+    __device__ const uint32_t *bm() const { return s.bm; }
+    __device__ AStarScratch &astar() { return s.astar; }
+    __device__ uint32_t sample_goal1(int lane) { // maze_generator.sample_goal(1)[0]
+        uint32_t g[2];
+        np_sample_goal(w, s, rng, e, 1, g, lane);
+        return g[0];
+    }
+    __device__ void plan_b(uint32_t acts[10], int lane) { // np.random.choice(all_actions, 10)
+        if (lane == 0)
+            for (int i = 0; i < 10; i++) acts[i] = rng.interval(3u);
+    }
+};
+struct PhiloxNavPolicy {
+    const World &w; int e; PhiloxNavScratch &s; Philox &rng;
+    __device__ const uint32_t *bm() const { return s.bm; }
+    __device__ AStarScratch &astar() { return s.astar; }
+    __device__ uint32_t sample_goal1(int lane) {
+        if (w.target_mode == T2D_TARGET_RPF) return rpf_next_goal(w, e, lane);
+        int nfree = bm_count_free(s.bm, lane);
+        return bm_select_free(s.bm, (int)rng.below((uint32_t)nfree), lane);
+    }
+    __device__ void plan_b(uint32_t acts[10], int) {
+        for (int i = 0; i < 10; i++) acts[i] = rng.interval(3u);
+    }
+};
+
+// Shared tail of Navigator.reset (navigator.py:38-63) and of the replan inside Navigator.step (:15-36):
+// A* to `goal`; while unsolvable or empty: up to 5 fresh goals; then plan B = 10 random actions.
+template <typename Policy>
+__device__ void nav_plan_from(const World &w, int e, Policy &P, int slot, int sr, int sc, uint32_t goal, int lane) {
+    int count_res = 0;
+    bool planb = false;
+    int len = astar_plan(w, e, P.bm(), P.astar(), slot, sr, sc, (int)(goal & 255u), (int)((goal >> 8) & 255u), lane);
+    while (len < 1) {
+        count_res++;
+        if (count_res > 5) { planb = true; break; }
+        goal = P.sample_goal1(lane);
+        len = astar_plan(w, e, P.bm(), P.astar(), slot, sr, sc, (int)(goal & 255u), (int)((goal >> 8) & 255u), lane);
+    }
+    if (planb) {
+        uint32_t acts[10];
+        P.plan_b(acts, lane);
+        if (lane == 0) nav_store_planb(w, e, acts);
+        len = 10;
+    }
+    if (lane == 0) {
+        w.nav_meta[e] = (uint32_t)len; // a_i = 0
+        w.nav_goal[e] = goal & 0xFFFFu;
+    }
+    __syncwarp();
+}
+
+// ---- Philox reset ----------------------------------------------------------------------------------
+// `nav` is non-NULL only for the Nav / RPF instantiation (it then also provides bm).
+template <typename ObsT>
+__device__ void reset_env_philox(const World &w, int e, uint32_t *bm, PhiloxNavScratch *nav, int slot, ObsT *obs, int lane, bool init_only) {
+    const uint32_t episode = w.episode[e];
+    Philox rng; // stream 0: the same on every lane (scalar decisions need no shuffles)
+    rng.init(w.seed, (uint32_t)e, episode, 0u);
+    bm_init(bm, w.H, w.W, lane);
+
+    if (w.map_type == T2D_MAP_MAZE) {
+        double r = w.level > 0 ? w.level * 0.02 : .03 * rng.dbl();
+        if (lane == 0) {
+            Philox walk;
+            walk.init(w.seed, (uint32_t)e, episode, 2u);
+            maze_walk(bm, walk, r);
+        }
+        __syncwarp();
+    } else {
+        double r = w.map_type == T2D_MAP_EMPTY ? 0.0 : (w.level > 0 ? w.level * 0.05 : 0.15 * rng.dbl());
+        int k = (int)(r * 6400.0); // generators.py:166
+        // Draw uniform interior cells until k distinct ones are set.  Processing a round of 32 draws in lane
+        // order (duplicates inside the round resolved to the lowest lane, surplus beyond k dropped from the
+        // high lanes) is the same process as drawing one at a time, i.e. a uniform k-subset.
+        Philox mine;
+        mine.init(w.seed, (uint32_t)e, episode, 0x100u + (uint32_t)lane);
+        int count = 0;
+        while (count < k) {
+            mine.block();
+            int cell = -1;
+#pragma unroll
+            for (int q = 0; q < 4; q++) { // first 13-bit candidate below 6400 (p(accept) = 0.78 each)
+                int cand = (int)(mine.out[q] & 8191u);
+                if (cell < 0 && cand < 6400) cell = cand;
+            }
+            mine.have = 0;
+            bool valid = cell >= 0;
+            uint32_t vmask = __ballot_sync(0xFFFFFFFFu, valid);
+            bool fresh = false;
+            int r_ = 0, c_ = 0;
+            if (valid) {
+                uint32_t peers = __match_any_sync(vmask, cell);
+                r_ = cell / 80 + 1;
+                c_ = cell - (r_ - 1) * 80 + 1;
+                fresh = (lane == __ffs(peers) - 1) && !bm_wall(bm, r_, c_);
+            }
+            uint32_t fmask = __ballot_sync(0xFFFFFFFFu, fresh);
+            int need = k - count;
+            int rank = __popc(fmask & ((1u << lane) - 1u));
+            if (fresh && rank < need) bm_set(bm, r_, c_);
+            count += min(need, __popc(fmask));
+            __syncwarp();
+        }
+    }
+
+    uint32_t *gm = w.maps + (size_t)e * T2D_MAP_WORDS;
+    for (int i = lane; i < T2D_MAP_WORDS; i += 32) gm[i] = bm[i];
+    if (w.target_mode == T2D_TARGET_RPF) {
+        uint32_t wallbits = rpf_clear_corners(bm, w.H, w.W, lane);
+        if (lane == 0) w.rpf[e] = wallbits << 8; // static_goals(): vector = 0
+        __syncwarp();
+    }
+
+    // spawn (generators.py:53-77): tracker uniform over free cells, target uniform over the free cells of the 2x2 block
+    int nfree = bm_count_free(bm, lane);
+    uint32_t tr;
+    uint32_t goals = 0;
+    if (w.target_mode == T2D_TARGET_RPF) {
+        uint32_t g = rpf_next_goal(w, e, lane); // sample_goal(2): one cursor step, both goals that corner
+        goals = g | (g << 16);
+        tr = rpf_corner(w.H, w.W, 0);
+    } else {
+        tr = bm_select_free(bm, (int)rng.below((uint32_t)nfree), lane);
+    }
+    int r0 = tr & 255, c0 = tr >> 8;
+    int cr[4], cc[4];
+    int m = around_free(bm, r0, c0, cr, cc);
+    int pick = (int)rng.below((uint32_t)m);
+    int r1 = cr[0], c1 = cc[0];
+#pragma unroll
+    for (int q = 1; q < 4; q++)
+        if (pick == q) { r1 = cr[q]; c1 = cc[q]; }
+    uint32_t p = (uint32_t)r0 | ((uint32_t)c0 << 8) | ((uint32_t)r1 << 16) | ((uint32_t)c1 << 24);
+
+    if (w.target_mode == T2D_TARGET_NAV) { // goals matter only to the Navigator (track_1v1.py:139-141)
+        // sample_goal(2): two distinct uniform free cells, redrawn while the tracker starts on one (track_1v1.py:237-240)
+        uint32_t g0, g1;
+        do {
+            int j0 = (int)rng.below((uint32_t)nfree);
+            int j1 = (int)rng.below((uint32_t)(nfree - 1));
+            if (j1 >= j0) j1++;
+            g0 = bm_select_free(bm, j0, lane);
+            g1 = bm_select_free(bm, j1, lane);
+        } while (g0 == tr || g1 == tr);
+        goals = g0 | (g1 << 16);
+    }
+
+    if (lane == 0) {
+        w.pos[e] = p;
+        w.goals[e] = goals;
+    }
+    if (!init_only) {
+        if (w.target_mode == T2D_TARGET_RAM) {
+            uint32_t word = ram_new_plan(rng, false, 0); // RamAgent.reset (navigator.py:90-93)
+            if (lane == 0) w.ram[e] = word;
+        }
+        if (nav) {
+            Philox nrng;
+            nrng.init(w.seed, (uint32_t)e, episode, 3u);
+            PhiloxNavPolicy P{w, e, *nav, nrng};
+            nav_plan_from(w, e, P, slot, r1, c1, goals >> 16, lane); // Navigator.reset(init_states[1], goal_states[1])
+        }
+        if (lane == 0) {
+            w.ctr[e] = 0;
+            w.episode[e] = episode + 1;
+        }
+        if (obs && w.obs_type == T2D_OBS_PARTIAL) {
+            if (w.target_mode == T2D_TARGET_RPF) { // observations come from the ENV map (corners not cleared)
+                __syncwarp();
+                for (int i = lane; i < T2D_MAP_WORDS; i += 32) bm[i] = gm[i];
+                __syncwarp();
+            }
+            write_partial_obs(bm, p, obs + (size_t)e * T2D_ENV_CELLS, lane);
+        }
+    }
+}
+
+template <typename ObsT>
+__global__ void __launch_bounds__(128) reset_philox_kernel(World w, const uint8_t *__restrict__ mask, int from_list, ObsT *obs, int init_only) {
+    __shared__ uint32_t bms[4][T2D_MAP_WORDS];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int gw = blockIdx.x * 4 + wib, nw = gridDim.x * 4;
+    if (from_list) {
+        const int n = (int)w.work_count[0];
+        for (int i = gw; i < n; i += nw) {
+            reset_env_philox<ObsT>(w, (int)w.work_list[i], bms[wib], nullptr, 0, obs, lane, init_only != 0);
+            __syncwarp();
+        }
+    } else {
+        for (int e = gw; e < w.E; e += nw) {
+            if (mask && !mask[e]) continue;
+            reset_env_philox<ObsT>(w, e, bms[wib], nullptr, 0, obs, lane, init_only != 0);
+            __syncwarp();
+        }
+    }
+}
+
+// Nav / RPF: one warp per CTA, A* scratch in shared memory
+template <typename ObsT>
+__global__ void __launch_bounds__(32) reset_philox_nav_kernel(World w, const uint8_t *__restrict__ mask, int from_list, ObsT *obs, int init_only) {
+    __shared__ PhiloxNavScratch s;
+    const int lane = threadIdx.x;
+    if (from_list) {
+        const int n = (int)w.work_count[0];
+        for (int i = blockIdx.x; i < n; i += gridDim.x) {
+            reset_env_philox<ObsT>(w, (int)w.work_list[i], s.bm, &s, blockIdx.x, obs, lane, init_only != 0);
+            __syncwarp();
+        }
+    } else {
+        for (int e = blockIdx.x; e < w.E; e += gridDim.x) {
+            if (mask && !mask[e]) continue;
+            reset_env_philox<ObsT>(w, e, s.bm, &s, blockIdx.x, obs, lane, init_only != 0);
+            __syncwarp();
+        }
+    }
+}
+
+// ---- numpy-compat reset ------------------------------------------------------------------------------
+template <typename ObsT>
+__device__ void reset_env_numpy(const World &w, int e, NumpyScratch &s, int slot, ObsT *obs, int lane, bool init_only) {
+    uint32_t *gkey = w.mt_key + (size_t)e * T2D_MT_N;
+    for (int i = lane; i < T2D_MT_N; i += 32) s.key[i] = gkey[i];
+    MtRng rng;
+    rng.key = s.key;
+    rng.pos = w.mt_pos[e];
+    __syncwarp();
+    // Only lane 0 draws; scalars it decides are broadcast with shuffles.
+    bm_init(s.bm, w.H, w.W, lane);
+
+    if (w.map_type == T2D_MAP_MAZE) {
+        if (lane == 0) {
+            double r = w.level > 0 ? w.level * 0.02 : .03 * rng.dbl(); // track_1v1.py:220-223
+            maze_walk(s.bm, rng, r);
+        }
+        __syncwarp();
+    } else {
+        int k = 0;
+        if (lane == 0) {
+            double r = w.map_type == T2D_MAP_EMPTY ? 0.0 : (w.level > 0 ? w.level * 0.05 : 0.15 * rng.dbl()); // :226-231
+            k = (int)(r * 6400.0);
+        }
+        k = __shfl_sync(0xFFFFFFFFu, k, 0);
+        np_permutation(s, rng, 6400, lane); // np.random.choice(6400, k, replace=False) == permutation(6400)[:k]
+        for (int t = lane; t < k; t += 32) {
+            int idx = s.perm[t];
+            bm_set(s.bm, idx / 80 + 1, idx % 80 + 1);
+        }
+        __syncwarp();
+    }
+
+    uint32_t *gm = w.maps + (size_t)e * T2D_MAP_WORDS;
+    for (int i = lane; i < T2D_MAP_WORDS; i += 32) gm[i] = s.bm[i];
+    if (w.target_mode == T2D_TARGET_RPF) {
+        uint32_t wallbits = rpf_clear_corners(s.bm, w.H, w.W, lane);
+        if (lane == 0) w.rpf[e] = wallbits << 8; // static_goals(): vector = 0
+        __syncwarp();
+    }
+
+    uint32_t g[2];
+    np_sample_goal(w, s, rng, e, 2, g, lane);
+
+    // sample_close_states(2, 1) (generators.py:53-77)
+    int n = np_free_list(s, w.H, w.W, lane);
+    np_permutation(s, rng, n, lane);
+    uint32_t tr;
+    if (w.target_mode != T2D_TARGET_RPF) {
+        int cell = s.freel[s.perm[0]];
+        tr = (uint32_t)(cell / w.W) | ((uint32_t)(cell % w.W) << 8);
+    } else {
+        tr = rpf_corner(w.H, w.W, 0);
+    }
+    int r0 = tr & 255, c0 = tr >> 8;
+    int cr[4], cc[4];
+    int m = around_free(s.bm, r0, c0, cr, cc);
+    int pick = 0;
+    if (lane == 0) { // permutation(m)[0] with m <= 4, in registers
+        int pm[4] = {0, 1, 2, 3};
+        for (int i = m - 1; i >= 1; i--) {
+            int j = (int)rng.interval((uint32_t)i);
+            int t = pm[i]; pm[i] = pm[j]; pm[j] = t;
+        }
+        pick = pm[0];
+    }
+    pick = __shfl_sync(0xFFFFFFFFu, pick, 0);
+    int r1 = cr[0], c1 = cc[0];
+#pragma unroll
+    for (int q = 1; q < 4; q++)
+        if (pick == q) { r1 = cr[q]; c1 = cc[q]; }
+    __syncwarp();
+    np_permutation(s, rng, n, lane); // sample_state(0): choice(n, size=0, replace=False) still shuffles (generators.py:28 via :73)
+
+    while (g[0] == tr || g[1] == tr) np_sample_goal(w, s, rng, e, 2, g, lane); // track_1v1.py:239-240
+
+    uint32_t p = (uint32_t)r0 | ((uint32_t)c0 << 8) | ((uint32_t)r1 << 16) | ((uint32_t)c1 << 24);
+    if (lane == 0) {
+        w.pos[e] = p;
+        w.goals[e] = g[0] | (g[1] << 16);
+    }
+    if (!init_only) {
+        if (w.target_mode == T2D_TARGET_RAM) {
+            if (lane == 0) w.ram[e] = ram_new_plan(rng, false, 0);
+        }
+        if (w.target_mode == T2D_TARGET_NAV || w.target_mode == T2D_TARGET_RPF) {
+            NumpyNavPolicy P{w, e, s, rng};
+            nav_plan_from(w, e, P, slot, r1, c1, g[1], lane); // Navigator.reset(init_states[1], goal_states[1])
+        }
+        if (lane == 0) {
+            w.ctr[e] = 0;
+            w.episode[e] = w.episode[e] + 1;
+        }
+        __syncwarp();
+        if (obs && w.obs_type == T2D_OBS_PARTIAL) {
+            if (w.target_mode == T2D_TARGET_RPF) { // observations come from the ENV map (corners not cleared)
+                for (int i = lane; i < T2D_MAP_WORDS; i += 32) s.bm[i] = gm[i];
+                __syncwarp();
+            }
+            write_partial_obs(s.bm, p, obs + (size_t)e * T2D_ENV_CELLS, lane);
+        }
+    }
+    __syncwarp();
+    for (int i = lane; i < T2D_MT_N; i += 32) gkey[i] = s.key[i];
+    if (lane == 0) w.mt_pos[e] = rng.pos;
+}
+
+template <typename ObsT>
+__global__ void __launch_bounds__(32) reset_numpy_kernel(World w, const uint8_t *__restrict__ mask, int from_list, ObsT *obs, int init_only) {
+    __shared__ NumpyScratch s;
+    const int lane = threadIdx.x;
+    if (from_list) {
+        const int n = (int)w.work_count[0];
+        for (int i = blockIdx.x; i < n; i += gridDim.x) {
+            reset_env_numpy<ObsT>(w, (int)w.work_list[i], s, blockIdx.x, obs, lane, init_only != 0);
+            __syncwarp();
+        }
+    } else {
+        for (int e = blockIdx.x; e < w.E; e += gridDim.x) {
+            if (mask && !mask[e]) continue;
+            reset_env_numpy<ObsT>(w, e, s, blockIdx.x, obs, lane, init_only != 0);
+            __syncwarp();
+        }
+    }
+}
+
+// ---- Navigator.step replan (navigator.py:15-36), run BEFORE the step kernel for envs whose plan is used up ----
+__global__ void nav_scan_kernel(World w) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= w.E) return;
+    uint32_t meta = w.nav_meta[e];
+    if ((meta >> 16) >= (meta & 0xFFFFu)) { // a_i >= len(plan_actions)
+        uint32_t slot = atomicAdd(&w.work_count[1], 1u);
+        w.work_list[w.E + slot] = (uint32_t)e;
+    }
+}
+
+// load the generator maze of env e (ENV map, RPF corners cleared) into shared memory
+__device__ __forceinline__ void load_gen_maze(const World &w, int e, uint32_t *bm, int lane) {
+    const uint32_t *gm = w.maps + (size_t)e * T2D_MAP_WORDS;
+    for (int i = lane; i < T2D_MAP_WORDS; i += 32) bm[i] = gm[i];
+    __syncwarp();
+    if (w.target_mode == T2D_TARGET_RPF) rpf_clear_corners(bm, w.H, w.W, lane);
+}
+
+__global__ void __launch_bounds__(32) nav_replan_numpy_kernel(World w) {
+    __shared__ NumpyScratch s;
+    const int lane = threadIdx.x;
+    const int n = (int)w.work_count[1];
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        const int e = (int)w.work_list[w.E + i];
+        uint32_t *gkey = w.mt_key + (size_t)e * T2D_MT_N;
+        for (int q = lane; q < T2D_MT_N; q += 32) s.key[q] = gkey[q];
+        MtRng rng;
+        rng.key = s.key;
+        rng.pos = w.mt_pos[e];
+        load_gen_maze(w, e, s.bm, lane);
+        NumpyNavPolicy P{w, e, s, rng};
+        uint32_t goal = P.sample_goal1(lane); // self.goal_states = maze_generator.sample_goal(1)[0]
+        uint32_t p = w.pos[e];
+        nav_plan_from(w, e, P, blockIdx.x, (int)(p >> 16) & 255, (int)(p >> 24), goal, lane); // from old_state[1]
+        for (int q = lane; q < T2D_MT_N; q += 32) gkey[q] = s.key[q];
+        if (lane == 0) w.mt_pos[e] = rng.pos;
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(32) nav_replan_philox_kernel(World w) {
+    __shared__ PhiloxNavScratch s;
+    const int lane = threadIdx.x;
+    const int n = (int)w.work_count[1];
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        const int e = (int)w.work_list[w.E + i];
+        Philox rng;
+        rng.init(w.seed, (uint32_t)e, w.episode[e], 0x20000u + (w.ctr[e] >> 16));
+        load_gen_maze(w, e, s.bm, lane);
+        PhiloxNavPolicy P{w, e, s, rng};
+        uint32_t goal = P.sample_goal1(lane);
+        uint32_t p = w.pos[e];
+        nav_plan_from(w, e, P, blockIdx.x, (int)(p >> 16) & 255, (int)(p >> 24), goal, lane);
+        __syncwarp();
+    }
+}
+
+__global__ void finish_replan_kernel(World w) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) w.work_count[1] = 0;
+}
+
+// np.random.seed(seed) for env `e`: mt19937_seed (init_genrand)
+__global__ void seed_numpy_kernel(World w, int first, int count, unsigned long long base_seed, int add_index) {
+    int e = first + blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= first + count) return;
+    uint32_t seed = (uint32_t)(base_seed + (add_index ? (unsigned long long)e : 0ull));
+    uint32_t *key = w.mt_key + (size_t)e * T2D_MT_N;
+    for (int pos = 0; pos < T2D_MT_N; pos++) {
+        key[pos] = seed;
+        seed = 1812433253u * (seed ^ (seed >> 30)) + (uint32_t)pos + 1u;
+    }
+    w.mt_pos[e] = T2D_MT_N;
+}
+
+__global__ void finish_reset_kernel(World w) { // after a list-driven auto-reset: account and clear the queue
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        w.stats[0] += w.work_count[0];
+        w.work_count[0] = 0;
+    }
+}
+
+} // namespace
+
+#define T2D_NAV_GRID (148 * 4)
+
+template <typename ObsT>
+static cudaError_t launch_reset_t(const World &w, const uint8_t *mask, int from_list, ObsT *obs, int init_only, cudaStream_t s) {
+    const bool nav = w.target_mode == T2D_TARGET_NAV || w.target_mode == T2D_TARGET_RPF;
+    if (w.rng_mode == T2D_RNG_NUMPY) {
+        int grid = from_list ? T2D_NAV_GRID : min(w.E, T2D_NAV_GRID);
+        reset_numpy_kernel<ObsT><<<grid, 32, 0, s>>>(w, mask, from_list, obs, init_only);
+    } else if (nav) {
+        int grid = from_list ? T2D_NAV_GRID : min(w.E, T2D_NAV_GRID);
+        reset_philox_nav_kernel<ObsT><<<grid, 32, 0, s>>>(w, mask, from_list, obs, init_only);
+    } else {
+        int grid = from_list ? 148 * 2 : min((w.E + 3) / 4, 148 * 8);
+        reset_philox_kernel<ObsT><<<grid, 128, 0, s>>>(w, mask, from_list, obs, init_only);
+    }
+    cudaError_t err = cudaGetLastError();
+    if (err == cudaSuccess && from_list) {
+        finish_reset_kernel<<<1, 32, 0, s>>>(w);
+        err = cudaGetLastError();
+    }
+    return err;
+}
+
+cudaError_t t2d_launch_reset_f32(const World &w, const uint8_t *mask, int from_list, float *obs, int init_only, cudaStream_t s) {
+    return launch_reset_t<float>(w, mask, from_list, obs, init_only, s);
+}
+cudaError_t t2d_launch_reset_u8(const World &w, const uint8_t *mask, int from_list, uint8_t *obs, int init_only, cudaStream_t s) {
+    return launch_reset_t<uint8_t>(w, mask, from_list, obs, init_only, s);
+}
+cudaError_t t2d_launch_seed_numpy(const World &w, int first, int count, unsigned long long seed, int add_index, cudaStream_t s) {
+    seed_numpy_kernel<<<(count + 127) / 128, 128, 0, s>>>(w, first, count, seed, add_index);
+    return cudaGetLastError();
+}
+// Navigator.step's replan for every env whose plan is exhausted (no-op for other target modes)
+cudaError_t t2d_launch_nav_replan(const World &w, cudaStream_t s) {
+    if (w.target_mode != T2D_TARGET_NAV && w.target_mode != T2D_TARGET_RPF) return cudaSuccess;
+    nav_scan_kernel<<<(w.E + 255) / 256, 256, 0, s>>>(w);
+    if (w.rng_mode == T2D_RNG_NUMPY) nav_replan_numpy_kernel<<<T2D_NAV_GRID, 32, 0, s>>>(w);
+    else nav_replan_philox_kernel<<<T2D_NAV_GRID, 32, 0, s>>>(w);
+    finish_replan_kernel<<<1, 32, 0, s>>>(w);
+    return cudaGetLastError();
+}
+int t2d_nav_slots() { return T2D_NAV_GRID; }

@@ -1,0 +1,176 @@
+/*
+ * track2d.h -- C ABI of libtrack2d.so: a batched, device-resident implementation of the reference's
+ * gym-track2d environment (zfw1226/active_tracking_rl, envs/gym-track2d) for NVIDIA B200 (sm_100a).
+ *
+ * The reference has no native FFI; its boundary is the Python gym protocol.  Each entry point below
+ * names the reference interface it stands in for (paths relative to the reference root, "envs/" =
+ * envs/gym-track2d/gym_track2d/envs/).  The Python side (active_tracking_rl_b200/) binds these with
+ * ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain C: opaque handle, raw pointers, sizes; no torch / C++ types.
+ *   - every function returns 0 on success or a negative T2D_E_* code; track2d_last_error() gives the
+ *     message for the calling thread.
+ *   - "_dev" pointers are device pointers on the handle's device, owned by the caller; `stream` is a
+ *     cudaStream_t passed as void* (NULL = legacy default stream).  Device entry points only enqueue
+ *     work on `stream`; they never synchronise the host.
+ *   - "_host" entry points take host pointers, do H2D -> kernels -> D2H on the handle's own stream and
+ *     return after the results are in the host buffers.
+ *   - one handle per device, driven from one host thread (like one gym env object per process).
+ *   - agent 0 = tracker, agent 1 = target; positions are (row, col) on the 82x82 (Block/Empty) or
+ *     81x81 (Maze) grid including the wall border; actions 0..3 = up, down, left, right
+ *     (envs/track_1v1.py:276).
+ */
+#ifndef TRACK2D_H
+#define TRACK2D_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TRACK2D_ABI_VERSION 1
+
+/* gym id grammar 'Track2D-{Map}{Obs}{Target}-v{level}' (gym_track2d/__init__.py:3-18) */
+enum { T2D_MAP_BLOCK = 0, T2D_MAP_MAZE = 1, T2D_MAP_EMPTY = 2 };
+enum { T2D_OBS_PARTIAL = 0, T2D_OBS_FULL = 1 };
+enum { T2D_TARGET_ADV = 0, T2D_TARGET_PZR = 1, T2D_TARGET_FAR = 2, T2D_TARGET_NAV = 3, T2D_TARGET_RAM = 4, T2D_TARGET_RPF = 5 };
+
+/* RNG behind map generation, spawn sampling and the scripted targets.
+ *   PHILOX : counter-based Philox4x32-10 keyed by (seed, env); parallel sampling algorithms with the
+ *            same distributions as the reference (throughput mode).
+ *   NUMPY  : per-env MT19937 driven through numpy's legacy RandomState algorithms in exactly the
+ *            reference's draw order; env e behaves like the reference after np.random.seed(seed + e)
+ *            (with its no-argument np.random.seed() calls neutralised).  Bit-exact parity mode. */
+enum { T2D_RNG_PHILOX = 0, T2D_RNG_NUMPY = 1 };
+
+enum {
+    T2D_FLAG_AUTO_RESET = 1, /* step(): envs that finish are reset in the same call and their obs replaced by the reset obs */
+    T2D_FLAG_KEEP_F64 = 2    /* keep the float64 rewards of the last step for track2d_get_rewards_f64 */
+};
+
+enum {
+    T2D_OK = 0,
+    T2D_E_INVALID = -1,   /* bad argument */
+    T2D_E_CUDA = -2,      /* CUDA runtime error (message has the cudaError string) */
+    T2D_E_UNSUPPORTED = -3,
+    T2D_E_STATE = -4      /* e.g. step before reset */
+};
+
+/* bits of the device status word (track2d_get_status) */
+enum {
+    T2D_STATUS_BAD_ACTION = 1,    /* an action outside 0..3 was seen (it was reduced mod 4) */
+    T2D_STATUS_PLAN_OVERFLOW = 2, /* an A* plan exceeded TRACK2D_NAV_MAXPLAN */
+    T2D_STATUS_ASTAR_REPLACE = 4, /* Frontier.replace condition observed (provably unreachable on a unit-cost grid) */
+    T2D_STATUS_HEAP_OVERFLOW = 8
+};
+
+#define TRACK2D_FOV 13            /* 2 * pob_size + 1, envs/track_1v1.py:17 */
+#define TRACK2D_NAV_MAXPLAN 1024  /* longest stored Navigator plan (actions) */
+#define TRACK2D_RAM_MAXPLAN 9     /* RamAgent plans have 1..9 actions, envs/navigator.py:85,91 */
+
+typedef struct track2d_env track2d_env;
+
+typedef struct track2d_config {
+    int32_t abi_version;       /* TRACK2D_ABI_VERSION */
+    int32_t num_envs;          /* E >= 1 */
+    int32_t map_type;          /* T2D_MAP_*     (kwargs of gym.make, gym_track2d/__init__.py:12-16) */
+    int32_t obs_type;          /* T2D_OBS_* */
+    int32_t target_mode;       /* T2D_TARGET_* */
+    int32_t level;             /* 0 = random density, >0 = fixed (envs/track_1v1.py:220-229) */
+    int32_t rng_mode;          /* T2D_RNG_* */
+    int32_t device;            /* CUDA device ordinal */
+    int32_t max_episode_steps; /* gym TimeLimit; 500 in every registered id (gym_track2d/__init__.py:17); <=0 disables */
+    int32_t flags;             /* T2D_FLAG_* */
+    uint64_t seed;
+} track2d_config;
+
+/* ---- lifetime ------------------------------------------------------------------------------- */
+
+/* gym.make(id): Track1v1Env.__init__ (envs/track_1v1.py:14-69) for num_envs envs.  Allocates the
+ * struct-of-arrays world state on cfg->device.  No map is drawn until the first reset. */
+int track2d_create(const track2d_config *cfg, track2d_env **out);
+/* env.close() */
+int track2d_destroy(track2d_env *env);
+const char *track2d_last_error(void);
+int track2d_abi_version(void);
+
+/* observation_space / define_observation (envs/track_1v1.py:252-262): cells per agent per env:
+ * 169 (Partial) or H*W (Full).  An obs buffer holds num_envs * 2 * cells floats, laid out
+ * [env][agent][row][col] -- the reference's (2, 1, h, w) per env, batched on a leading axis. */
+int track2d_obs_cells(const track2d_env *env);
+int track2d_num_envs(const track2d_env *env);
+int track2d_map_height(const track2d_env *env);
+int track2d_map_width(const track2d_env *env);
+
+/* ---- device-resident API (caller-owned device buffers, stream-ordered, no host sync) --------- */
+
+/* Track1v1Env.reset (envs/track_1v1.py:134-168) + TimeLimit.reset, for every env whose mask byte is
+ * non-zero (mask_dev == NULL: all envs).  Writes the reset observations of those envs into obs_dev
+ * (float32 [E][2][cells]; other envs' rows are left untouched).  obs_dev may be NULL. */
+int track2d_reset(track2d_env *env, const uint8_t *mask_dev, float *obs_dev, void *stream);
+
+/* Track1v1Env.step (envs/track_1v1.py:71-127) + gym 0.12.5 TimeLimit.step, for all envs.
+ *   actions_dev : int32 [E][2]  (tracker, target); the target entry is ignored for Ram/Nav/RPF
+ *   obs_dev     : float32 [E][2][cells], 16-byte aligned  (environment.py:146 casts to float32)
+ *   reward_dev  : float32 [E][2]  (r_track, r_target; player_util.py:58 casts to float32)
+ *   done_dev    : uint8 [E]       (far-counter done OR elapsed >= max_episode_steps)
+ * With T2D_FLAG_AUTO_RESET, finished envs are then reset and their obs rows replaced. */
+int track2d_step(track2d_env *env, const int32_t *actions_dev, float *obs_dev, float *reward_dev, uint8_t *done_dev, void *stream);
+
+/* Same transition, observations written as uint8 (values 0,1,2,4) instead of float32 -- a lower
+ * traffic path for consumers that convert on load.  Not the contract dtype; reported separately. */
+int track2d_step_u8(track2d_env *env, const int32_t *actions_dev, uint8_t *obs_dev, float *reward_dev, uint8_t *done_dev, void *stream);
+int track2d_reset_u8(track2d_env *env, const uint8_t *mask_dev, uint8_t *obs_dev, void *stream);
+
+/* ---- host-buffer API (what a numpy-facing gym user calls; H2D/D2H inside) -------------------- */
+int track2d_reset_host(track2d_env *env, const uint8_t *mask_host, float *obs_host);
+int track2d_step_host(track2d_env *env, const int32_t *actions_host, float *obs_host, float *reward_host, uint8_t *done_host);
+
+/* ---- state read-back / injection (host pointers, synchronous; parity tests and the gym shim) -- */
+
+/* maps as uint8 [count][H][W], 1 = wall (Track1v1Env.maze) */
+int track2d_get_maps(track2d_env *env, int32_t first, int32_t count, uint8_t *maze_host);
+int track2d_set_maps(track2d_env *env, int32_t first, int32_t count, const uint8_t *maze_host);
+/* positions int32 [count][2][2] (Track1v1Env.state); counters int32 [count][2] = (C_far, elapsed_steps) */
+int track2d_get_agents(track2d_env *env, int32_t first, int32_t count, int32_t *pos_host, int32_t *counters_host);
+int track2d_set_agents(track2d_env *env, int32_t first, int32_t count, const int32_t *pos_host, const int32_t *counters_host);
+/* goal_states int32 [count][2][2] (envs/track_1v1.py:237) */
+int track2d_get_goals(track2d_env *env, int32_t first, int32_t count, int32_t *goals_host);
+/* RamAgent.plan_actions / a_i (envs/navigator.py:73-93): plan int32 [count][TRACK2D_RAM_MAXPLAN], len, idx int32 [count] */
+int track2d_get_ram(track2d_env *env, int32_t first, int32_t count, int32_t *plan_host, int32_t *len_host, int32_t *idx_host);
+int track2d_set_ram(track2d_env *env, int32_t first, int32_t count, const int32_t *plan_host, const int32_t *len_host, const int32_t *idx_host);
+/* Navigator.plan_actions / a_i / goal_states (envs/navigator.py:5-63): plan int32 [count][TRACK2D_NAV_MAXPLAN] */
+int track2d_get_nav(track2d_env *env, int32_t first, int32_t count, int32_t *plan_host, int32_t *len_host, int32_t *idx_host, int32_t *goal_host);
+int track2d_set_nav(track2d_env *env, int32_t first, int32_t count, const int32_t *plan_host, const int32_t *len_host, const int32_t *idx_host, const int32_t *goal_host);
+/* float64 rewards of the last step, [E][2] (needs T2D_FLAG_KEEP_F64): exactly what Track1v1Env.step returns */
+int track2d_get_rewards_f64(track2d_env *env, int32_t first, int32_t count, double *rewards_host);
+/* the action the target actually executed in the last step (Ram/Nav/RPF override), int32 [count] */
+int track2d_get_target_actions(track2d_env *env, int32_t first, int32_t count, int32_t *actions_host);
+/* T2D_RNG_NUMPY: np.random.seed(seed) for one env / read its MT19937 state (key[624], pos) */
+int track2d_seed_env(track2d_env *env, int32_t index, uint32_t seed);
+int track2d_get_rng_numpy(track2d_env *env, int32_t index, uint32_t *key_host, int32_t *pos_host);
+/* Track1v1Env.__init__ draws one map it never uses (envs/track_1v1.py:45); in T2D_RNG_NUMPY mode the
+ * gym shim calls this so that `np.random.seed(s); gym.make(id); reset()` stays stream-exact. */
+int track2d_init_maze(track2d_env *env, const uint8_t *mask_dev, void *stream);
+/* OR of T2D_STATUS_* seen so far (synchronises the handle's device work on `stream`) */
+int track2d_get_status(track2d_env *env, uint32_t *status_host, void *stream);
+/* number of envs reset by the last auto-reset step / episodes finished so far (synchronous) */
+int track2d_get_counters(track2d_env *env, uint64_t *episodes_done, uint64_t *steps_done);
+
+/* ---- learner kernels on the same stream (reference: shared_optim.py:122-175, player_util.py:157) */
+
+/* clip_grad_norm_(params, max_norm) followed by SharedAdam.step (AMSGrad, eps added AFTER the sqrt,
+ * old-style bias correction) over one flat fp32 parameter vector.  All pointers are device pointers
+ * of n floats; `step` is the 1-based update count (state['step'] after the increment);
+ * `grad_scale` multiplies the gradient first (1/world_size after a sum-allreduce).
+ * `norm_scratch_dev` is one float of scratch (the squared global norm). */
+int track2d_sharedadam_step(float *param_dev, const float *grad_dev, float *exp_avg_dev, float *exp_avg_sq_dev,
+                            float *max_exp_avg_sq_dev, int64_t n, int64_t step, double lr, double beta1, double beta2,
+                            double eps, double max_grad_norm, double grad_scale, float *norm_scratch_dev, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRACK2D_H */
