@@ -212,7 +212,7 @@ int track2d_create(const track2d_config *cfg, track2d_env **out) {
     ALLOC(w.rpf, E);
     ALLOC(w.tgt_act, E);
     ALLOC(w.work_list, 2 * (size_t)E);
-    ALLOC(w.work_count, 2);
+    ALLOC(w.work_count, 4);
     ALLOC(w.status, 1);
     ALLOC(w.stats, 2);
     ALLOC(w.nav_meta, E);

@@ -46,7 +46,7 @@ struct World {
     double *rew64;       // [E][2] or NULL
     uint8_t *tgt_act;    // [E]
     uint32_t *work_list; // [E] env indices queued for reset / replan
-    uint32_t *work_count;// [2]: [0] resets queued, [1] replans queued
+    uint32_t *work_count;// [4]: [0] resets queued, [1] replans queued, [2] reset-kernel CTA ticket
     uint32_t *status;    // [1] OR of T2D_STATUS_*
     unsigned long long *stats; // [2] episodes finished, env-steps done
     uint8_t *astar_ws;   // A* workspace (Nav/RPF only)
@@ -57,7 +57,7 @@ struct World {
 __device__ __forceinline__ int map_word_index(int r, int c) { return (r + T2D_PAD) * T2D_ROW_WORDS + ((c + T2D_PAD) >> 5); }
 __device__ __forceinline__ uint32_t map_bit_of(int c) { return 1u << ((c + T2D_PAD) & 31); }
 __device__ __forceinline__ int map_is_wall(const uint32_t *__restrict__ m, int r, int c) {
-    return (m[map_word_index(r, c)] >> ((c + T2D_PAD) & 31)) & 1u;
+    return (__ldg(m + map_word_index(r, c)) >> ((c + T2D_PAD) & 31)) & 1u;
 }
 // 13 wall bits of padded row `pr`, starting at padded column `pc` (0..81)
 __device__ __forceinline__ uint32_t map_row13(const uint32_t *__restrict__ m, int pr, int pc) {

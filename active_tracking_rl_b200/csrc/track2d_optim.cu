@@ -76,6 +76,34 @@ __global__ void __launch_bounds__(256) sharedadam_kernel(float *__restrict__ p, 
         for (int64_t j = i; j < n; j++) adam_one(p[j], g[j] * coef, m[j], v[j], vmax[j], b1, b2, eps, neg_step);
 }
 
+
+// Agent.optimize's backward recursion (player_util.py:127-140) for E envs x 2 agents, T steps:
+//   R_t   = r_t + gamma * R_{t+1}            (R_T = bootstrap value, 0 where the episode ended)
+//   gae_t = gamma * tau * gae_{t+1} + r_t + gamma * V_{t+1} - V_t
+// with both recursions cut where done_t = 1 (the reference never lets a rollout span episodes,
+// train.py:85-88).  rewards/values/returns/gae are [T(+1)][E][2] floats, done is [T][E] bytes.
+__global__ void __launch_bounds__(256) gae_kernel(const float *__restrict__ rewards, const uint8_t *__restrict__ done,
+                                                  const float *__restrict__ values, float *__restrict__ returns,
+                                                  float *__restrict__ gae_out, int T, int64_t E, float gamma, float tau) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; // (env, agent) pair
+    if (i >= 2 * E) return;
+    int64_t e = i >> 1;
+    float R = values[(int64_t)T * 2 * E + i];
+    float vnext = R;
+    float gae = 0.f;
+    for (int t = T - 1; t >= 0; t--) {
+        float r = rewards[(int64_t)t * 2 * E + i];
+        float v = values[(int64_t)t * 2 * E + i];
+        if (done[(int64_t)t * E + e]) { R = 0.f; vnext = 0.f; gae = 0.f; }
+        R = gamma * R + r;
+        float delta = r + gamma * vnext - v;
+        gae = gae * gamma * tau + delta;
+        returns[(int64_t)t * 2 * E + i] = R;
+        gae_out[(int64_t)t * 2 * E + i] = gae;
+        vnext = v;
+    }
+}
+
 } // namespace
 
 void t2d_set_error(const char *fmt, ...);
@@ -107,6 +135,21 @@ extern "C" int track2d_sharedadam_step(float *param, const float *grad, float *e
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) {
         t2d_set_error("track2d_sharedadam_step: %s", cudaGetErrorString(err));
+        return T2D_E_CUDA;
+    }
+    return T2D_OK;
+}
+
+extern "C" int track2d_gae_returns(const float *rewards, const uint8_t *done, const float *values, float *returns, float *gae,
+                                   int32_t T, int64_t E, double gamma, double tau, void *stream) {
+    if (!rewards || !done || !values || !returns || !gae || T < 1 || E < 1) {
+        t2d_set_error("track2d_gae_returns: bad argument");
+        return T2D_E_INVALID;
+    }
+    gae_kernel<<<(unsigned)((2 * E + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rewards, done, values, returns, gae, T, E, (float)gamma, (float)tau);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) {
+        t2d_set_error("track2d_gae_returns: %s", cudaGetErrorString(err));
         return T2D_E_CUDA;
     }
     return T2D_OK;

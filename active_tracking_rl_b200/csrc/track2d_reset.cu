@@ -140,6 +140,23 @@ __device__ void write_partial_obs(const uint32_t *bm, uint32_t p, ObsT *__restri
     }
 }
 
+// after a list-driven auto-reset the LAST CTA to finish accounts the episodes and clears the queue
+// (every CTA has read work_count[0] by then), so no extra launch is needed
+__device__ __forceinline__ void finish_reset(const World &w) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        uint32_t t = atomicAdd(&w.work_count[2], 1u);
+        if (t == gridDim.x - 1) {
+            w.stats[0] += w.work_count[0];
+            w.work_count[0] = 0;
+            w.work_count[2] = 0;
+            __threadfence();
+        }
+    }
+}
+
+
 // ---- numpy legacy sampling helpers (T2D_RNG_NUMPY) ------------------------------------------------------
 // perm / freel (numpy sampling) and the A* maps are never live at the same time: one union.
 struct NumpyScratch {
@@ -317,6 +334,25 @@ __device__ void reset_env_philox(const World &w, int e, uint32_t *bm, PhiloxNavS
         Philox mine;
         mine.init(w.seed, (uint32_t)e, episode, 0x100u + (uint32_t)lane);
         int count = 0;
+        // bulk rounds: 4 candidates per lane (128 draws) while even an all-fresh round cannot overshoot k; the
+        // old value of the shared-memory atomicOr says whether the cell was new
+        while (k - count >= 128) {
+            mine.block();
+            int added = 0;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                int cand = (int)(mine.out[q] & 8191u);
+                if (cand < 6400) {
+                    int rr = cand / 80 + 1, cq = cand - (rr - 1) * 80 + 1;
+                    uint32_t bit = map_bit_of(cq);
+                    uint32_t old = atomicOr(&bm[map_word_index(rr, cq)], bit);
+                    added += (old & bit) ? 0 : 1;
+                }
+            }
+            mine.have = 0;
+            count += __reduce_add_sync(0xFFFFFFFFu, added);
+        }
+        __syncwarp();
         while (count < k) {
             mine.block();
             int cell = -1;
@@ -428,6 +464,7 @@ __global__ void __launch_bounds__(128) reset_philox_kernel(World w, const uint8_
             reset_env_philox<ObsT>(w, (int)w.work_list[i], bms[wib], nullptr, 0, obs, lane, init_only != 0);
             __syncwarp();
         }
+        finish_reset(w);
     } else {
         for (int e = gw; e < w.E; e += nw) {
             if (mask && !mask[e]) continue;
@@ -448,6 +485,7 @@ __global__ void __launch_bounds__(32) reset_philox_nav_kernel(World w, const uin
             reset_env_philox<ObsT>(w, (int)w.work_list[i], s.bm, &s, blockIdx.x, obs, lane, init_only != 0);
             __syncwarp();
         }
+        finish_reset(w);
     } else {
         for (int e = blockIdx.x; e < w.E; e += gridDim.x) {
             if (mask && !mask[e]) continue;
@@ -574,6 +612,7 @@ __global__ void __launch_bounds__(32) reset_numpy_kernel(World w, const uint8_t 
             reset_env_numpy<ObsT>(w, (int)w.work_list[i], s, blockIdx.x, obs, lane, init_only != 0);
             __syncwarp();
         }
+        finish_reset(w);
     } else {
         for (int e = blockIdx.x; e < w.E; e += gridDim.x) {
             if (mask && !mask[e]) continue;
@@ -658,13 +697,6 @@ __global__ void seed_numpy_kernel(World w, int first, int count, unsigned long l
     w.mt_pos[e] = T2D_MT_N;
 }
 
-__global__ void finish_reset_kernel(World w) { // after a list-driven auto-reset: account and clear the queue
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        w.stats[0] += w.work_count[0];
-        w.work_count[0] = 0;
-    }
-}
-
 } // namespace
 
 #define T2D_NAV_GRID (148 * 4)
@@ -679,15 +711,10 @@ static cudaError_t launch_reset_t(const World &w, const uint8_t *mask, int from_
         int grid = from_list ? T2D_NAV_GRID : min(w.E, T2D_NAV_GRID);
         reset_philox_nav_kernel<ObsT><<<grid, 32, 0, s>>>(w, mask, from_list, obs, init_only);
     } else {
-        int grid = from_list ? 148 * 2 : min((w.E + 3) / 4, 148 * 8);
+        int grid = from_list ? 148 * 4 : min((w.E + 3) / 4, 148 * 8);
         reset_philox_kernel<ObsT><<<grid, 128, 0, s>>>(w, mask, from_list, obs, init_only);
     }
-    cudaError_t err = cudaGetLastError();
-    if (err == cudaSuccess && from_list) {
-        finish_reset_kernel<<<1, 32, 0, s>>>(w);
-        err = cudaGetLastError();
-    }
-    return err;
+    return cudaGetLastError();
 }
 
 cudaError_t t2d_launch_reset_f32(const World &w, const uint8_t *mask, int from_list, float *obs, int init_only, cudaStream_t s) {

@@ -27,7 +27,33 @@ struct ObsStore;
 
 template <>
 struct ObsStore<float> {
-    // words of staged bytes [0, nwords) -> floats; dst is 16-byte aligned
+    // words of staged bytes [0, nwords) -> floats; dst is 16-byte aligned.  UNROLL independent LDS are issued
+    // before the converts and stores so one shared-memory latency covers UNROLL stores.  Stores are
+    // streaming (st.global.cs): the observation tensor is written once per step and must not push the
+    // bit-packed maps out of L2.
+    template <int WORDS, int THREADS>
+    static __device__ __forceinline__ void run_full(const uint32_t *sobs, float *dst, int tid) {
+        float4 *d4 = reinterpret_cast<float4 *>(dst);
+        constexpr int ITERS = (WORDS + THREADS - 1) / THREADS;
+        uint32_t w[ITERS];
+#pragma unroll
+        for (int i = 0; i < ITERS; i++) {
+            int q = tid + i * THREADS;
+            w[i] = (q < WORDS) ? sobs[q] : 0u;
+        }
+#pragma unroll
+        for (int i = 0; i < ITERS; i++) {
+            int q = tid + i * THREADS;
+            if (q < WORDS) {
+                float4 v;
+                v.x = (float)(w[i] & 0xFFu);
+                v.y = (float)((w[i] >> 8) & 0xFFu);
+                v.z = (float)((w[i] >> 16) & 0xFFu);
+                v.w = (float)(w[i] >> 24);
+                __stcs(d4 + q, v);
+            }
+        }
+    }
     static __device__ __forceinline__ void run(const uint32_t *sobs, float *dst, int nwords, int tid, int nthreads) {
         float4 *d4 = reinterpret_cast<float4 *>(dst);
         for (int q = tid; q < nwords; q += nthreads) {
@@ -37,7 +63,7 @@ struct ObsStore<float> {
             v.y = (float)((w >> 8) & 0xFFu);
             v.z = (float)((w >> 16) & 0xFFu);
             v.w = (float)(w >> 24);
-            d4[q] = v;
+            __stcs(d4 + q, v);
         }
     }
     static __device__ __forceinline__ void tail(const uint32_t *sobs, float *dst, int first_word, int ncells_tail, int tid) {
@@ -48,12 +74,31 @@ struct ObsStore<float> {
 
 template <>
 struct ObsStore<uint8_t> {
-    static __device__ __forceinline__ void run(const uint32_t *sobs, uint8_t *dst, int nwords, int tid, int nthreads) {
+    template <int WORDS, int THREADS>
+    static __device__ __forceinline__ void run_full(const uint32_t *sobs, uint8_t *dst, int tid) {
         // dst is 16-byte aligned when the chunk starts at a multiple of 8 envs (338 * 8 = 169 * 16)
+        static_assert(WORDS % 4 == 0, "uint8 chunks are whole uint4s");
+        constexpr int W4 = WORDS / 4;
+        constexpr int ITERS = (W4 + THREADS - 1) / THREADS;
+        uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+        const uint4 *s4 = reinterpret_cast<const uint4 *>(sobs);
+        uint4 w[ITERS];
+#pragma unroll
+        for (int i = 0; i < ITERS; i++) {
+            int q = tid + i * THREADS;
+            w[i] = (q < W4) ? s4[q] : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int i = 0; i < ITERS; i++) {
+            int q = tid + i * THREADS;
+            if (q < W4) __stcs(d4 + q, w[i]);
+        }
+    }
+    static __device__ __forceinline__ void run(const uint32_t *sobs, uint8_t *dst, int nwords, int tid, int nthreads) {
         uint4 *d4 = reinterpret_cast<uint4 *>(dst);
         const uint4 *s4 = reinterpret_cast<const uint4 *>(sobs);
         int n4 = nwords >> 2;
-        for (int q = tid; q < n4; q += nthreads) d4[q] = s4[q];
+        for (int q = tid; q < n4; q += nthreads) __stcs(d4 + q, s4[q]);
         uint32_t *d1 = reinterpret_cast<uint32_t *>(dst);
         for (int q = (n4 << 2) + tid; q < nwords; q += nthreads) d1[q] = sobs[q];
     }
@@ -147,9 +192,15 @@ __global__ void __launch_bounds__(THREADS) step_kernel(World w, const int32_t *_
     if (w.obs_type != T2D_OBS_PARTIAL || obs == nullptr) return; // Full observations are written by full_obs_kernel
 
     // ---- phase B: 13-bit window rows -> bytes, 4 rows (52 B = 13 words) per thread -----------------
+    // All eight map-word loads of a group are issued before any is used (no branches in between: envs past
+    // the end of the batch are clamped onto the last valid env and masked afterwards), so a group costs one
+    // memory latency, not four.
     constexpr int GROUPS = (26 * N) / 4;
+#pragma unroll 1
     for (int g = tid; g < GROUPS; g += THREADS) {
-        uint32_t mrow[4];
+        uint32_t lo_w[4], hi_w[4];
+        int sh[4];
+        bool ok[4];
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             int R = 4 * g + i;
@@ -157,11 +208,20 @@ __global__ void __launch_bounds__(THREADS) step_kernel(World w, const int32_t *_
             int rem = R - 26 * el;
             int a = rem >= 13;
             int wr = rem - 13 * a;
+            ok[i] = el < nenv;
+            el = min(el, nenv - 1);
             uint32_t p = spos[el];
             int r = a ? (p >> 16) & 255 : p & 255;
             int c = a ? p >> 24 : (p >> 8) & 255;
-            mrow[i] = el < nenv ? map_row13(w.maps + (size_t)(env0 + el) * T2D_MAP_WORDS, r + wr, c) : 0u;
+            const uint32_t *row = w.maps + (size_t)(env0 + el) * T2D_MAP_WORDS + (r + wr) * T2D_ROW_WORDS;
+            int wi = c >> 5;
+            lo_w[i] = __ldg(row + wi);
+            hi_w[i] = __ldg(row + (wi < 2 ? wi + 1 : 2));
+            sh[i] = c & 31;
         }
+        uint32_t mrow[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) mrow[i] = ok[i] ? (__funnelshift_r(lo_w[i], hi_w[i], sh[i]) & 0x1FFFu) : 0u;
         uint32_t lo = mrow[0] | (mrow[1] << 13) | (mrow[2] << 26);
         uint32_t hi = (mrow[2] >> 6) | (mrow[3] << 7);
         uint32_t *dst = sobs + 13 * g;
@@ -188,10 +248,14 @@ __global__ void __launch_bounds__(THREADS) step_kernel(World w, const int32_t *_
     __syncthreads();
 
     // ---- phase D: coalesced 16-byte stores ---------------------------------------------------------
-    const int ncells = nenv * T2D_ENV_CELLS;
     ObsT *dst = obs + (size_t)env0 * T2D_ENV_CELLS;
-    ObsStore<ObsT>::run(sobs, dst, ncells >> 2, tid, THREADS);
-    if (ncells & 3) ObsStore<ObsT>::tail(sobs, dst, ncells >> 2, ncells & 3, tid);
+    if (nenv == N) {
+        ObsStore<ObsT>::template run_full<(T2D_ENV_CELLS * N) / 4, THREADS>(sobs, dst, tid);
+    } else {
+        const int ncells = nenv * T2D_ENV_CELLS;
+        ObsStore<ObsT>::run(sobs, dst, ncells >> 2, tid, THREADS);
+        if (ncells & 3) ObsStore<ObsT>::tail(sobs, dst, ncells >> 2, ncells & 3, tid);
+    }
 }
 
 // Full observations (obs_type 'Full', track_1v1.py:288-290): both agents get the whole map with the
@@ -217,14 +281,10 @@ __global__ void full_obs_kernel(World w, ObsT *__restrict__ obs, const uint8_t *
 
 template <int TARGET, int RNG, typename ObsT>
 cudaError_t launch_step_t(const World &w, const int32_t *actions, ObsT *obs, float *reward, uint8_t *done, cudaStream_t s) {
-    // big batches: 64 envs / CTA (21.6 KB staging); small batches: 16 envs / CTA so the grid still covers the SMs
-    if (w.E >= 148 * 64 * 2) {
-        constexpr int N = 64, T = 128;
-        step_kernel<TARGET, RNG, ObsT, N, T><<<(w.E + N - 1) / N, T, 0, s>>>(w, actions, obs, reward, done);
-    } else {
-        constexpr int N = 16, T = 64;
-        step_kernel<TARGET, RNG, ObsT, N, T><<<(w.E + N - 1) / N, T, 0, s>>>(w, actions, obs, reward, done);
-    }
+    // 16 envs per CTA of 128 threads: 104 four-row groups -> at most one group per thread (a single load
+    // latency in phase B), 5.4 KB of staging, 16 CTAs (2048 threads) resident per SM.
+    constexpr int N = 16, T = 128;
+    step_kernel<TARGET, RNG, ObsT, N, T><<<(w.E + N - 1) / N, T, 0, s>>>(w, actions, obs, reward, done);
     return cudaGetLastError();
 }
 

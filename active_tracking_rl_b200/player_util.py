@@ -1,0 +1,172 @@
+"""Agent (player_util.py:9-161) for E envs at once: rollout buffers, action_train / action_test, reset,
+update_rnn_hiden and optimize, with the reference's per-env arithmetic.
+
+Differences forced by batching (hard part 3):
+  * a reference rollout stops at `done` and the worker resets before the next one (train.py:73-88);
+    here every rollout has exactly num_steps steps, finished envs are reset inside env.step, and the
+    return / GAE recursions, the bootstrap value and the LSTM state are cut at those boundaries -- so
+    for each env the loss is the sum of the reference's losses over the episode segments in the window;
+  * the 16 Hogwild workers' separate updates become ONE update with the mean of the per-env gradients.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+
+class Agent(object):
+    def __init__(self, model, env, args, state, device):
+        self.model = model
+        self.env = env
+        self.args = args
+        self.device = torch.device(device)
+        self.num_agents = len(env.observation_space)
+        self.num_envs = env.num_envs
+        self.dim_action = 1
+        self.rnn_out = args.rnn_out
+        self.w_entropy_target = getattr(args, 'entropy_target', 0.2)
+        self.gpu_id = self.device.index if self.device.type == 'cuda' else -1
+        self.state = state
+        self.eps_len = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
+        self.n_steps = 0  # env-steps taken (all envs)
+        self.done = None
+        self.reward = None
+        self.info = None
+        self.hxs = torch.zeros(self.num_envs, self.num_agents, self.rnn_out, device=self.device)
+        self.cxs = torch.zeros(self.num_envs, self.num_agents, self.rnn_out, device=self.device)
+        self.lib = _lib.load() if self.device.type == 'cuda' else None
+        self._alloc_rollout()
+        self.clear_actions()
+
+    # ---- rollout storage -------------------------------------------------------------------------
+    def _alloc_rollout(self):
+        T, E = int(self.args.num_steps), self.num_envs
+        obs_shape = tuple(self.env.obs.shape[1:])
+        # the env writes straight into these (no copies): obs_buf[t + 1] <- step t
+        self.obs_buf = torch.zeros((T + 1, E) + obs_shape, dtype=torch.float32, device=self.device)
+        self.rew_buf = torch.zeros((T, E, 2), dtype=torch.float32, device=self.device)
+        self.done_buf = torch.zeros((T, E), dtype=torch.uint8, device=self.device)
+        self.val_buf = torch.zeros((T + 1, E, 2), dtype=torch.float32, device=self.device)
+        self.ret_buf = torch.zeros((T, E, 2), dtype=torch.float32, device=self.device)
+        self.gae_buf = torch.zeros((T, E, 2), dtype=torch.float32, device=self.device)
+        self.t = 0
+
+    def clear_actions(self):
+        self.values, self.log_probs, self.entropies, self.preds = [], [], [], []
+        self.t = 0
+        return self
+
+    # ---- episode / recurrent state ---------------------------------------------------------------
+    def reset(self):
+        """env.reset() for every env + zero LSTM state (player_util.py:84-102)"""
+        self.env.reset()
+        self.obs_buf[0].copy_(self.env.obs)
+        self.state = self.obs_buf[0]
+        self.eps_len.zero_()
+        self.reset_rnn_hiden()
+        self.clear_actions()
+
+    def reset_rnn_hiden(self):
+        self.hxs = torch.zeros(self.num_envs, self.num_agents, self.rnn_out, device=self.device)
+        self.cxs = torch.zeros(self.num_envs, self.num_agents, self.rnn_out, device=self.device)
+
+    def update_rnn_hiden(self):
+        """truncate BPTT at the rollout boundary (player_util.py:104-106)"""
+        self.hxs = self.hxs.detach()
+        self.cxs = self.cxs.detach()
+
+    # ---- acting ----------------------------------------------------------------------------------
+    def action_train(self, forced_actions=None):
+        """one step of every env: policy forward -> env.step -> buffers (player_util.py:44-67)"""
+        t = self.t
+        assert t < self.rew_buf.shape[0], "rollout buffer full: call optimize()"
+        value, action, entropy, log_prob, (hxs, cxs), R_pred = self.model((self.state, (self.hxs, self.cxs)), False, forced_actions)
+        actions32 = action.to(torch.int32).contiguous()
+        self.env.step_into(actions32, self.obs_buf[t + 1], self.rew_buf[t], self.done_buf[t])
+        self.reward = self.rew_buf[t]
+        self.done = self.done_buf[t]
+        self.state = self.obs_buf[t + 1]
+        # envs that finished were reset by the env: their next step starts from zero LSTM state (train.py:73-74)
+        keep = (1 - self.done.to(hxs.dtype)).view(-1, 1, 1)
+        self.hxs, self.cxs = hxs * keep, cxs * keep
+        self.eps_len = (self.eps_len + 1) * (1 - self.done.to(torch.int32))
+        self.n_steps += self.num_envs
+        self.values.append(value)
+        self.entropies.append(entropy)
+        self.log_probs.append(log_prob)
+        self.preds.append(R_pred)
+        self.last_actions = actions32
+        self.t = t + 1
+        return self
+
+    def action_test(self):
+        """greedy step (player_util.py:69-82); used by the evaluator"""
+        with torch.no_grad():
+            value, action, entropy, log_prob, (hxs, cxs), R_pred = self.model((self.state, (self.hxs, self.cxs)), True)
+        actions32 = action.to(torch.int32).contiguous()
+        obs, reward, done = self.env.step(actions32)
+        self.reward, self.done = reward, done
+        self.obs_buf[0].copy_(obs)
+        self.state = self.obs_buf[0]
+        keep = (1 - done.to(hxs.dtype)).view(-1, 1, 1)
+        self.hxs, self.cxs = hxs * keep, cxs * keep
+        self.eps_len = (self.eps_len + 1) * (1 - done.to(torch.int32))
+        self.n_steps += self.num_envs
+        return self
+
+    # ---- learning --------------------------------------------------------------------------------
+    def _returns_and_gae(self, T):
+        E = self.num_envs
+        if self.lib is not None:
+            p = lambda x: C.c_void_p(x.data_ptr())  # noqa: E731
+            _lib.check(self.lib.track2d_gae_returns(p(self.rew_buf), p(self.done_buf), p(self.val_buf), p(self.ret_buf), p(self.gae_buf),
+                                                    T, E, float(self.args.gamma), float(self.args.tau),
+                                                    C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)), self.lib)
+        else:
+            raise _lib.Track2DError("Agent.optimize needs the CUDA library; there is no CPU fallback")
+        return self.ret_buf[:T], self.gae_buf[:T]
+
+    def optimize(self, params, optimizer, shared_model, training_mode, device_share=None, world_size=1, allreduce=None):
+        """Agent.optimize (player_util.py:108-161): bootstrap, n-step return + GAE, A3C losses of both agents,
+        aux reward-prediction L1, backward, (all-reduce), clip 50 + SharedAdam.  `params`, `shared_model` and
+        `device_share` are accepted for call compatibility: the model IS the shared model here."""
+        T, E = self.t, self.num_envs
+        assert T > 0
+        with torch.no_grad():  # player_util.py:110-116, value only matters where the episode is still running
+            v_boot, _, _, _, _, _ = self.model((self.state, (self.hxs, self.cxs)))
+            self.val_buf[T].copy_(v_boot)
+            self.val_buf[:T].copy_(torch.stack([v.detach() for v in self.values], 0))
+        returns, gae = self._returns_and_gae(T)
+
+        values = torch.stack(self.values, 0)        # (T, E, 2)
+        log_probs = torch.stack(self.log_probs, 0)  # (T, E, 2)
+        entropies = torch.stack(self.entropies, 0)  # (T, E, 2)
+        w_ent = torch.tensor([float(self.args.entropy), float(self.w_entropy_target)], device=self.device)
+        advantage = returns - values
+        value_loss = (0.5 * advantage.pow(2)).sum(0)                       # (E, 2)   :133
+        policy_loss = (-(log_probs * gae) - w_ent * entropies).sum(0)      # (E, 2)   :137-139
+        loss_tracker = policy_loss[:, 0] + 0.5 * value_loss[:, 0]          # :143
+        loss_target = policy_loss[:, 1] + 0.5 * value_loss[:, 1]
+        pred_loss = torch.zeros(E, device=self.device)
+        use_aux = 'reward' in self.args.aux and self.preds[0] is not None
+        if use_aux:  # L1 between the target's prediction and the TRACKER's reward (:128-129)
+            preds = torch.stack(self.preds, 0).squeeze(-1)                 # (T, E)
+            pred_loss = (preds - self.rew_buf[:T, :, 0]).abs().sum(0)
+        if training_mode == 0:
+            loss = loss_tracker
+        elif training_mode == 1:
+            loss = loss_target
+        else:
+            loss = loss_tracker + loss_target
+        if use_aux and training_mode != 0:
+            loss = loss + pred_loss
+        optimizer.zero_grad()
+        loss.mean().backward()  # mean over envs == average of the per-worker gradients
+        if allreduce is not None and world_size > 1:
+            allreduce(optimizer.fp.grad)
+        optimizer.step(max_grad_norm=50.0, grad_scale=1.0 / world_size)
+        self.clear_actions()
+        self.obs_buf[0].copy_(self.state)
+        self.state = self.obs_buf[0]
+        return policy_loss.detach(), value_loss.detach(), entropies.detach().sum(0), pred_loss.detach()

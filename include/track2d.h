@@ -170,6 +170,12 @@ int track2d_sharedadam_step(float *param_dev, const float *grad_dev, float *exp_
                             float *max_exp_avg_sq_dev, int64_t n, int64_t step, double lr, double beta1, double beta2,
                             double eps, double max_grad_norm, double grad_scale, float *norm_scratch_dev, void *stream);
 
+/* The backward recursion of Agent.optimize (player_util.py:127-140) for all envs: n-step returns R_t and
+ * GAE advantages, cut at episode ends.  rewards [T][E][2], done [T][E], values [T+1][E][2] (row T = the
+ * bootstrap value V(s_T), ignored where done[T-1]); outputs returns, gae [T][E][2].  Device pointers. */
+int track2d_gae_returns(const float *rewards_dev, const uint8_t *done_dev, const float *values_dev, float *returns_dev,
+                        float *gae_dev, int32_t T, int64_t E, double gamma, double tau, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
