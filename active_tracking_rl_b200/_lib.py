@@ -37,6 +37,7 @@ SYMBOLS = {
     "track2d_destroy": (C.c_int, [_vp]),
     "track2d_last_error": (C.c_char_p, []),
     "track2d_abi_version": (C.c_int, []),
+    "track2d_launch_count": (C.c_uint64, []),
     "track2d_obs_cells": (C.c_int, [_vp]),
     "track2d_num_envs": (C.c_int, [_vp]),
     "track2d_map_height": (C.c_int, [_vp]),

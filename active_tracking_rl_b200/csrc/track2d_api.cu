@@ -22,6 +22,8 @@ cudaError_t t2d_launch_nav_replan(const World &w, cudaStream_t s);
 int t2d_nav_slots();
 
 static thread_local char g_err[512] = "";
+static unsigned long long g_launches = 0; // kernels of this library enqueued so far (host-side count)
+void t2d_count_launches(int n) { g_launches += (unsigned long long)n; }
 
 void t2d_set_error(const char *fmt, ...) {
     va_list ap;
@@ -104,6 +106,7 @@ int do_reset(track2d_env *env, const uint8_t *mask, ObsT *obs, int init_only, cu
     if (sizeof(ObsT) == 4) err = t2d_launch_reset_f32(w, mask, 0, (float *)obs, init_only, s);
     else err = t2d_launch_reset_u8(w, mask, 0, (uint8_t *)obs, init_only, s);
     T2D_CUDA(err);
+    t2d_count_launches(1);
     if (!init_only && obs && w.obs_type == T2D_OBS_FULL) {
         if (sizeof(ObsT) == 4) err = t2d_launch_full_obs_f32(w, (float *)obs, mask, s);
         else err = t2d_launch_full_obs_u8(w, (uint8_t *)obs, mask, s);
@@ -125,9 +128,11 @@ int do_step(track2d_env *env, const int32_t *actions, ObsT *obs, float *reward, 
     T2D_REQUIRE(((uintptr_t)actions & 7u) == 0 && ((uintptr_t)reward & 7u) == 0, "step: actions/reward buffers must be 8-byte aligned");
     cudaError_t err;
     T2D_CUDA(t2d_launch_nav_replan(w, s));
+    if (w.target_mode == T2D_TARGET_NAV || w.target_mode == T2D_TARGET_RPF) t2d_count_launches(3);
     if (sizeof(ObsT) == 4) err = t2d_launch_step_f32(w, actions, (float *)obs, reward, done, s);
     else err = t2d_launch_step_u8(w, actions, (uint8_t *)obs, reward, done, s);
     T2D_CUDA(err);
+    t2d_count_launches(1 + ((w.flags & T2D_FLAG_AUTO_RESET) ? 1 : 0));
     if (obs && w.obs_type == T2D_OBS_FULL) {
         if (sizeof(ObsT) == 4) err = t2d_launch_full_obs_f32(w, (float *)obs, nullptr, s);
         else err = t2d_launch_full_obs_u8(w, (uint8_t *)obs, nullptr, s);
@@ -170,6 +175,7 @@ void unpack_map(const uint32_t *words, int H, int W, uint8_t *maze) {
 extern "C" {
 
 const char *track2d_last_error(void) { return g_err; }
+uint64_t track2d_launch_count(void) { return g_launches; }
 int track2d_abi_version(void) { return TRACK2D_ABI_VERSION; }
 
 int track2d_create(const track2d_config *cfg, track2d_env **out) {

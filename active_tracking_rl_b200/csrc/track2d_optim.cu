@@ -107,6 +107,7 @@ __global__ void __launch_bounds__(256) gae_kernel(const float *__restrict__ rewa
 } // namespace
 
 void t2d_set_error(const char *fmt, ...);
+void t2d_count_launches(int n);
 
 extern "C" int track2d_sharedadam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, float *max_exp_avg_sq,
                                        int64_t n, int64_t step, double lr, double beta1, double beta2, double eps, double max_grad_norm,
@@ -120,6 +121,7 @@ extern "C" int track2d_sharedadam_step(float *param, const float *grad, float *e
         return T2D_E_INVALID;
     }
     cudaStream_t s = (cudaStream_t)stream;
+    t2d_count_launches(max_grad_norm > 0.0 ? 2 : 1);
     int grid = (int)((n / 4 + 255) / 256);
     if (grid < 1) grid = 1;
     if (grid > 148 * 8) grid = 148 * 8;
@@ -146,6 +148,7 @@ extern "C" int track2d_gae_returns(const float *rewards, const uint8_t *done, co
         t2d_set_error("track2d_gae_returns: bad argument");
         return T2D_E_INVALID;
     }
+    t2d_count_launches(1);
     gae_kernel<<<(unsigned)((2 * E + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rewards, done, values, returns, gae, T, E, (float)gamma, (float)tau);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) {

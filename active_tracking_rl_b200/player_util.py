@@ -26,6 +26,10 @@ class Agent(object):
         self.dim_action = 1
         self.rnn_out = args.rnn_out
         self.w_entropy_target = getattr(args, 'entropy_target', 0.2)
+        # the reference's clip_grad_norm_(params, 50) never clips: `params` is the generator train.py:39-44 makes
+        # once, consumed by the first call while the shared grads are still None (pinned by
+        # the golden-vector tests).  0 reproduces that effective behaviour, 50 is the written intent.
+        self.max_grad_norm = float(getattr(args, 'max_grad_norm', 0.0))
         self.gpu_id = self.device.index if self.device.type == 'cuda' else -1
         self.state = state
         self.eps_len = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
@@ -77,13 +81,24 @@ class Agent(object):
         self.cxs = self.cxs.detach()
 
     # ---- acting ----------------------------------------------------------------------------------
-    def action_train(self, forced_actions=None):
-        """one step of every env: policy forward -> env.step -> buffers (player_util.py:44-67)"""
+    def action_train(self, forced_actions=None, host=None):
+        """one step of every env: policy forward -> env.step -> buffers (player_util.py:44-67).
+        host=None: device-resident (the env kernel writes straight into the rollout buffers).
+        host=<pinned buffers from env.alloc_host_buffers()>: the reference's data flow -- actions to host
+        numpy, env.step on host buffers (C ABI: H2D, kernels, D2H), observation back to the device
+        (player_util.py:54-59 `torch.from_numpy(state_multi).float().to(device)`)."""
         t = self.t
         assert t < self.rew_buf.shape[0], "rollout buffer full: call optimize()"
         value, action, entropy, log_prob, (hxs, cxs), R_pred = self.model((self.state, (self.hxs, self.cxs)), False, forced_actions)
         actions32 = action.to(torch.int32).contiguous()
-        self.env.step_into(actions32, self.obs_buf[t + 1], self.rew_buf[t], self.done_buf[t])
+        if host is None:
+            self.env.step_into(actions32, self.obs_buf[t + 1], self.rew_buf[t], self.done_buf[t])
+        else:
+            host['actions'].copy_(actions32)  # D2H, synchronous
+            self.env.step_host(host['actions'], host['obs'], host['reward'], host['done'])
+            self.obs_buf[t + 1].copy_(host['obs'], non_blocking=True)  # H2D from pinned memory
+            self.rew_buf[t].copy_(host['reward'], non_blocking=True)
+            self.done_buf[t].copy_(host['done'], non_blocking=True)
         self.reward = self.rew_buf[t]
         self.done = self.done_buf[t]
         self.state = self.obs_buf[t + 1]
@@ -127,14 +142,15 @@ class Agent(object):
             raise _lib.Track2DError("Agent.optimize needs the CUDA library; there is no CPU fallback")
         return self.ret_buf[:T], self.gae_buf[:T]
 
-    def optimize(self, params, optimizer, shared_model, training_mode, device_share=None, world_size=1, allreduce=None):
+    def optimize(self, params, optimizer, shared_model, training_mode, device_share=None, world_size=1, allreduce=None,
+                 boot_forced_actions=None):
         """Agent.optimize (player_util.py:108-161): bootstrap, n-step return + GAE, A3C losses of both agents,
-        aux reward-prediction L1, backward, (all-reduce), clip 50 + SharedAdam.  `params`, `shared_model` and
+        aux reward-prediction L1, backward, (all-reduce), [clip] + SharedAdam.  `params`, `shared_model` and
         `device_share` are accepted for call compatibility: the model IS the shared model here."""
         T, E = self.t, self.num_envs
         assert T > 0
         with torch.no_grad():  # player_util.py:110-116, value only matters where the episode is still running
-            v_boot, _, _, _, _, _ = self.model((self.state, (self.hxs, self.cxs)))
+            v_boot, _, _, _, _, _ = self.model((self.state, (self.hxs, self.cxs)), False, boot_forced_actions)
             self.val_buf[T].copy_(v_boot)
             self.val_buf[:T].copy_(torch.stack([v.detach() for v in self.values], 0))
         returns, gae = self._returns_and_gae(T)
@@ -165,7 +181,7 @@ class Agent(object):
         loss.mean().backward()  # mean over envs == average of the per-worker gradients
         if allreduce is not None and world_size > 1:
             allreduce(optimizer.fp.grad)
-        optimizer.step(max_grad_norm=50.0, grad_scale=1.0 / world_size)
+        optimizer.step(max_grad_norm=self.max_grad_norm, grad_scale=1.0 / world_size)
         self.clear_actions()
         self.obs_buf[0].copy_(self.state)
         self.state = self.obs_buf[0]

@@ -1,0 +1,143 @@
+"""The synchronous on-device actor-learner that replaces the reference's W Hogwild worker processes
+(main.py:102-116, train.py:15-113): E envs per GPU advance in lock step -- policy.step and env.step
+alternate on one CUDA stream with no host round trip -- and every num_steps steps ONE update is applied.
+Across GPUs (one process each) the env shards are independent; the only exchange is one NCCL
+all-reduce of the flat gradient per rollout, after which every rank applies the identical fused
+SharedAdam update (so the replicas stay bit-identical without ever broadcasting weights again).
+
+    python -m active_tracking_rl_b200.train --env Track2D-BlockPartialPZR-v0 --num-envs 65536 --iters 100
+    torchrun --nproc-per-node 8 -m active_tracking_rl_b200.train ...
+"""
+import argparse
+import os
+import time
+
+import torch
+
+from .environment import create_env
+from .model import build_model
+from .player_util import Agent
+from .shared_optim import SharedAdam
+
+
+def make_parser():
+    """the flags of main.py:16-50 (same names and defaults) + the batched-run additions"""
+    p = argparse.ArgumentParser(description='A3C (synchronous, batched, on-device)')
+    p.add_argument('--lr', type=float, default=0.001)
+    p.add_argument('--gamma', type=float, default=0.9)
+    p.add_argument('--tau', type=float, default=1.00)
+    p.add_argument('--entropy', type=float, default=0.01)
+    p.add_argument('--entropy-target', type=float, default=0.2)
+    p.add_argument('--seed', type=int, default=1)
+    p.add_argument('--workers', type=int, default=1, help='kept for CLI compatibility; parallelism is --num-envs')
+    p.add_argument('--num-steps', type=int, default=20)
+    p.add_argument('--test-eps', type=int, default=100)
+    p.add_argument('--env', default='Track2D-BlockPartialPZR-v0')
+    p.add_argument('--env-base', default='Track2D-BlockPartialNav-v0')
+    p.add_argument('--optimizer', default='Adam')
+    p.add_argument('--amsgrad', default=True)
+    p.add_argument('--load-model-dir', default=None)
+    p.add_argument('--log-dir', default='logs/')
+    p.add_argument('--network', default='tat-maze-lstm')
+    p.add_argument('--aux', default='reward')
+    p.add_argument('--shared-optimizer', dest='shared_optimizer', action='store_true')
+    p.add_argument('--split', dest='split', action='store_true')
+    p.add_argument('--train-mode', type=int, default=-1)
+    p.add_argument('--stack-frames', type=int, default=1)
+    p.add_argument('--rnn-out', type=int, default=128)
+    p.add_argument('--max-step', type=int, default=150000)
+    p.add_argument('--init-step', type=int, default=-1)
+    # batched-run additions
+    p.add_argument('--num-envs', type=int, default=4096, help='envs per GPU')
+    p.add_argument('--iters', type=int, default=100, help='rollout+update iterations to run')
+    p.add_argument('--max-grad-norm', type=float, default=0.0,
+                   help='0 = the reference\'s effective behaviour (its clip_grad_norm_(params, 50) is inert); 50 = its intent')
+    p.add_argument('--tf32', action='store_true', help='allow TF32 tensor-core math in the policy (off: float32 like the reference)')
+    return p
+
+
+def default_args(**kw):
+    args = make_parser().parse_args([])
+    args.single = False
+    args.rescale = False
+    for k, v in kw.items():
+        setattr(args, k, v)
+    return args
+
+
+class Trainer(object):
+    def __init__(self, args, device, rank=0, world_size=1, rng="philox"):
+        self.args, self.device, self.rank, self.world_size = args, torch.device(device), rank, world_size
+        # the reference computes in float32; keep cuDNN / cuBLAS from silently dropping to TF32
+        torch.backends.cudnn.allow_tf32 = bool(getattr(args, 'tf32', False))
+        torch.backends.cuda.matmul.allow_tf32 = bool(getattr(args, 'tf32', False))
+        if not hasattr(args, 'single'):
+            args.single = False
+        self.env = create_env(args.env, args, num_envs=args.num_envs, device=self.device, seed=args.seed + rank, rng=rng)
+        torch.manual_seed(args.seed)  # identical initial weights on every rank (the reference shares ONE model)
+        self.model = build_model(self.env.observation_space, self.env.action_space, args, self.device).to(self.device)
+        if args.load_model_dir is not None:
+            self.model.load_state_dict(torch.load(args.load_model_dir, map_location=self.device))
+        torch.manual_seed(args.seed + rank)  # train.py:20: per-worker sampling stream
+        torch.cuda.manual_seed(args.seed + rank)
+        if args.train_mode == 0:
+            params = self.model.player0.parameters()
+        elif args.train_mode == 1:
+            params = self.model.player1.parameters()
+        else:
+            params = self.model.parameters()
+        self.optimizer = SharedAdam(params, lr=args.lr, amsgrad=args.amsgrad)
+        self.player = Agent(self.model, self.env, args, None, self.device)
+        self.player.w_entropy_target = args.entropy_target
+        self.player.max_grad_norm = float(getattr(args, 'max_grad_norm', 0.0))
+        self.player.reset()
+        self.n_iter = 0
+        self.allreduce = None
+        if world_size > 1:
+            import torch.distributed as dist
+            self.allreduce = lambda g: dist.all_reduce(g, op=dist.ReduceOp.SUM)
+
+    def iteration(self, training_mode=None, host=None):
+        """train.py:69-95 for all envs: detach LSTM state, num_steps x (policy.step, env.step), optimize.
+        host: pinned host buffers -> every env.step goes through the host-buffer C ABI (see Agent.action_train)."""
+        mode = self.args.train_mode if training_mode is None else training_mode
+        p = self.player
+        p.update_rnn_hiden()
+        for _ in range(self.args.num_steps):
+            p.action_train(host=host)
+        out = p.optimize(None, self.optimizer, self.model, mode, None, world_size=self.world_size, allreduce=self.allreduce)
+        self.n_iter += 1
+        return out
+
+    def env_steps_per_iteration(self):
+        return self.args.num_steps * self.args.num_envs
+
+    def save(self, path):
+        torch.save(self.model.state_dict(), path)
+
+
+def main():
+    args = make_parser().parse_args()
+    args.single = False
+    rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl')
+    tr = Trainer(args, 'cuda:%d' % local_rank, rank, world)
+    t0 = time.time()
+    for it in range(args.iters):
+        pl, vl, ent, prl = tr.iteration()
+        if rank == 0 and (it % 10 == 0 or it == args.iters - 1):
+            torch.cuda.synchronize()
+            sps = (it + 1) * tr.env_steps_per_iteration() * world / (time.time() - t0)
+            print('iter %d  policy_loss %.4f %.4f  value_loss %.4f %.4f  pred_loss %.4f  reward %.4f  env-steps/s %.3e' % (
+                it, pl[:, 0].mean(), pl[:, 1].mean(), vl[:, 0].mean(), vl[:, 1].mean(), prl.mean(), tr.player.rew_buf[:, :, 0].mean(), sps))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -95,6 +95,8 @@ int track2d_create(const track2d_config *cfg, track2d_env **out);
 int track2d_destroy(track2d_env *env);
 const char *track2d_last_error(void);
 int track2d_abi_version(void);
+/* number of this library's kernels enqueued so far in this process (host-side count; bench.py's gpu_launches) */
+uint64_t track2d_launch_count(void);
 
 /* observation_space / define_observation (envs/track_1v1.py:252-262): cells per agent per env:
  * 169 (Partial) or H*W (Full).  An obs buffer holds num_envs * 2 * cells floats, laid out

@@ -198,4 +198,4 @@ class Worker(object):
         # the generator train.py:39-44 creates once; the first call consumes it while the shared grads are still
         # None, every later call sees an exhausted generator (pinned by tests/golden/learner_*.npz).
         shared_adam_step(self.sd, gd, self.adam_state, lr=self.lr)
-        return float(loss)
+        return float(loss.detach())

@@ -75,7 +75,7 @@ def record(name, env_id, network, aux, train_mode, entropy_target, env_seed, ite
     torch.Tensor.multinomial = scripted
 
     rec = dict(obs=[], actions=[], rewards=[], dones=[], values=[], log_probs=[], entropies=[], preds=[], iter_len=[], iter_done=[],
-               policy_loss=[], value_loss=[], pred_loss=[], boot=[], grad_norm=[], grad_sum=[], param_sum=[], param_norm=[], reset_before=[])
+               policy_loss=[], value_loss=[], pred_loss=[], boot_actions=[], grad_norm=[], grad_sum=[], param_sum=[], param_norm=[], reset_before=[])
     names = list(shared_model.state_dict().keys())
     try:
         np.random.seed(env_seed)
@@ -109,10 +109,10 @@ def record(name, env_id, network, aux, train_mode, entropy_target, env_seed, ite
                     break
             rec['iter_len'].append(n)
             rec['iter_done'].append(bool(player.done))
-            if not player.done:
-                k0 = len(taken)
+            k0 = len(taken)
             pl, vl, ent, prl = player.optimize(params, optimizer, shared_model, train_mode, device)
-            rec['boot'].append(player_boot(player))
+            # the bootstrap forward inside optimize() SAMPLES actions; the tracker's one feeds the TAT target's value
+            rec['boot_actions'].append(taken[k0:k0 + 2] if len(taken) >= k0 + 2 else [-1, -1])
             rec['policy_loss'].append(pl.detach().numpy().reshape(2))
             rec['value_loss'].append(vl.detach().numpy().reshape(2))
             rec['pred_loss'].append(float(prl.sum().item()))
@@ -128,7 +128,7 @@ def record(name, env_id, network, aux, train_mode, entropy_target, env_seed, ite
             rec['param_norm'].append([float(ssd[k].double().norm()) for k in names])
     finally:
         torch.Tensor.multinomial = orig_multinomial
-    out = {k: np.asarray(v) for k, v in rec.items() if k != 'boot'}
+    out = {k: np.asarray(v) for k, v in rec.items()}
     out['param_names'] = np.asarray(names)
     out['grad_names'] = np.asarray([n for n, _ in player.model.named_parameters()])
     out['meta'] = np.asarray([env_id, network, aux, str(train_mode), str(entropy_target), str(env_seed), str(scale)])
@@ -138,10 +138,6 @@ def record(name, env_id, network, aux, train_mode, entropy_target, env_seed, ite
     np.savez_compressed(path, **out)
     print('%-18s iters=%d steps=%d dones=%s total_grad_norm=%s  %.1f KB' % (name, iters, len(rec['dones']), rec['iter_done'],
                                                                           ['%.1f' % g for g in total_gn], os.path.getsize(path) / 1024))
-
-
-def player_boot(player):
-    return 0
 
 
 if __name__ == '__main__':
