@@ -310,14 +310,14 @@ __device__ void nav_plan_from(const World &w, int e, Policy &P, int slot, int sr
 
 // ---- Philox reset ----------------------------------------------------------------------------------
 // `nav` is non-NULL only for the Nav / RPF instantiation (it then also provides bm).
-template <typename ObsT>
-__device__ void reset_env_philox(const World &w, int e, uint32_t *bm, PhiloxNavScratch *nav, int slot, ObsT *obs, int lane, bool init_only) {
+template <typename ObsT, int MAP>
+__device__ __noinline__ void reset_env_philox(const World &w, int e, uint32_t *bm, PhiloxNavScratch *nav, int slot, ObsT *obs, int lane, bool init_only) {
     const uint32_t episode = w.episode[e];
     Philox rng; // stream 0: the same on every lane (scalar decisions need no shuffles)
     rng.init(w.seed, (uint32_t)e, episode, 0u);
     bm_init(bm, w.H, w.W, lane);
 
-    if (w.map_type == T2D_MAP_MAZE) {
+    if (MAP == T2D_MAP_MAZE) {
         double r = w.level > 0 ? w.level * 0.02 : .03 * rng.dbl();
         if (lane == 0) {
             Philox walk;
@@ -326,7 +326,7 @@ __device__ void reset_env_philox(const World &w, int e, uint32_t *bm, PhiloxNavS
         }
         __syncwarp();
     } else {
-        double r = w.map_type == T2D_MAP_EMPTY ? 0.0 : (w.level > 0 ? w.level * 0.05 : 0.15 * rng.dbl());
+        double r = MAP == T2D_MAP_EMPTY ? 0.0 : (w.level > 0 ? w.level * 0.05 : 0.15 * rng.dbl());
         int k = (int)(r * 6400.0); // generators.py:166
         // Draw uniform interior cells until k distinct ones are set.  Processing a round of 32 draws in lane
         // order (duplicates inside the round resolved to the lowest lane, surplus beyond k dropped from the
@@ -453,51 +453,41 @@ __device__ void reset_env_philox(const World &w, int e, uint32_t *bm, PhiloxNavS
     }
 }
 
-template <typename ObsT>
+template <typename ObsT, int MAP>
 __global__ void __launch_bounds__(128) reset_philox_kernel(World w, const uint8_t *__restrict__ mask, int from_list, ObsT *obs, int init_only) {
     __shared__ uint32_t bms[4][T2D_MAP_WORDS];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int gw = blockIdx.x * 4 + wib, nw = gridDim.x * 4;
-    if (from_list) {
-        const int n = (int)w.work_count[0];
-        for (int i = gw; i < n; i += nw) {
-            reset_env_philox<ObsT>(w, (int)w.work_list[i], bms[wib], nullptr, 0, obs, lane, init_only != 0);
-            __syncwarp();
-        }
-        finish_reset(w);
-    } else {
-        for (int e = gw; e < w.E; e += nw) {
-            if (mask && !mask[e]) continue;
-            reset_env_philox<ObsT>(w, e, bms[wib], nullptr, 0, obs, lane, init_only != 0);
-            __syncwarp();
-        }
+    const int n = from_list ? (int)w.work_count[0] : w.E;
+    for (int i = gw; i < n; i += nw) {
+        int e = i;
+        if (from_list) e = (int)w.work_list[i];
+        else if (mask && !mask[e]) continue;
+        reset_env_philox<ObsT, MAP>(w, e, bms[wib], nullptr, 0, obs, lane, init_only != 0);
+        __syncwarp();
     }
+    if (from_list) finish_reset(w);
 }
 
 // Nav / RPF: one warp per CTA, A* scratch in shared memory
-template <typename ObsT>
+template <typename ObsT, int MAP>
 __global__ void __launch_bounds__(32) reset_philox_nav_kernel(World w, const uint8_t *__restrict__ mask, int from_list, ObsT *obs, int init_only) {
     __shared__ PhiloxNavScratch s;
     const int lane = threadIdx.x;
-    if (from_list) {
-        const int n = (int)w.work_count[0];
-        for (int i = blockIdx.x; i < n; i += gridDim.x) {
-            reset_env_philox<ObsT>(w, (int)w.work_list[i], s.bm, &s, blockIdx.x, obs, lane, init_only != 0);
-            __syncwarp();
-        }
-        finish_reset(w);
-    } else {
-        for (int e = blockIdx.x; e < w.E; e += gridDim.x) {
-            if (mask && !mask[e]) continue;
-            reset_env_philox<ObsT>(w, e, s.bm, &s, blockIdx.x, obs, lane, init_only != 0);
-            __syncwarp();
-        }
+    const int n = from_list ? (int)w.work_count[0] : w.E;
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        int e = i;
+        if (from_list) e = (int)w.work_list[i];
+        else if (mask && !mask[e]) continue;
+        reset_env_philox<ObsT, MAP>(w, e, s.bm, &s, blockIdx.x, obs, lane, init_only != 0);
+        __syncwarp();
     }
+    if (from_list) finish_reset(w);
 }
 
 // ---- numpy-compat reset ------------------------------------------------------------------------------
 template <typename ObsT>
-__device__ void reset_env_numpy(const World &w, int e, NumpyScratch &s, int slot, ObsT *obs, int lane, bool init_only) {
+__device__ __noinline__ void reset_env_numpy(const World &w, int e, NumpyScratch &s, int slot, ObsT *obs, int lane, bool init_only) {
     uint32_t *gkey = w.mt_key + (size_t)e * T2D_MT_N;
     for (int i = lane; i < T2D_MT_N; i += 32) s.key[i] = gkey[i];
     MtRng rng;
@@ -606,20 +596,15 @@ template <typename ObsT>
 __global__ void __launch_bounds__(32) reset_numpy_kernel(World w, const uint8_t *__restrict__ mask, int from_list, ObsT *obs, int init_only) {
     __shared__ NumpyScratch s;
     const int lane = threadIdx.x;
-    if (from_list) {
-        const int n = (int)w.work_count[0];
-        for (int i = blockIdx.x; i < n; i += gridDim.x) {
-            reset_env_numpy<ObsT>(w, (int)w.work_list[i], s, blockIdx.x, obs, lane, init_only != 0);
-            __syncwarp();
-        }
-        finish_reset(w);
-    } else {
-        for (int e = blockIdx.x; e < w.E; e += gridDim.x) {
-            if (mask && !mask[e]) continue;
-            reset_env_numpy<ObsT>(w, e, s, blockIdx.x, obs, lane, init_only != 0);
-            __syncwarp();
-        }
+    const int n = from_list ? (int)w.work_count[0] : w.E;
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        int e = i;
+        if (from_list) e = (int)w.work_list[i];
+        else if (mask && !mask[e]) continue;
+        reset_env_numpy<ObsT>(w, e, s, blockIdx.x, obs, lane, init_only != 0);
+        __syncwarp();
     }
+    if (from_list) finish_reset(w);
 }
 
 // ---- Navigator.step replan (navigator.py:15-36), run BEFORE the step kernel for envs whose plan is used up ----
@@ -701,20 +686,31 @@ __global__ void seed_numpy_kernel(World w, int first, int count, unsigned long l
 
 #define T2D_NAV_GRID (148 * 4)
 
+template <typename ObsT, int MAP>
+static cudaError_t launch_reset_map(const World &w, const uint8_t *mask, int from_list, ObsT *obs, int init_only, cudaStream_t s) {
+    const bool nav = w.target_mode == T2D_TARGET_NAV || w.target_mode == T2D_TARGET_RPF;
+    if (nav) {
+        int grid = from_list ? T2D_NAV_GRID : min(w.E, T2D_NAV_GRID);
+        reset_philox_nav_kernel<ObsT, MAP><<<grid, 32, 0, s>>>(w, mask, from_list, obs, init_only);
+    } else {
+        int grid = from_list ? 148 * 4 : min((w.E + 3) / 4, 148 * 8);
+        reset_philox_kernel<ObsT, MAP><<<grid, 128, 0, s>>>(w, mask, from_list, obs, init_only);
+    }
+    return cudaGetLastError();
+}
+
 template <typename ObsT>
 static cudaError_t launch_reset_t(const World &w, const uint8_t *mask, int from_list, ObsT *obs, int init_only, cudaStream_t s) {
-    const bool nav = w.target_mode == T2D_TARGET_NAV || w.target_mode == T2D_TARGET_RPF;
     if (w.rng_mode == T2D_RNG_NUMPY) {
         int grid = from_list ? T2D_NAV_GRID : min(w.E, T2D_NAV_GRID);
         reset_numpy_kernel<ObsT><<<grid, 32, 0, s>>>(w, mask, from_list, obs, init_only);
-    } else if (nav) {
-        int grid = from_list ? T2D_NAV_GRID : min(w.E, T2D_NAV_GRID);
-        reset_philox_nav_kernel<ObsT><<<grid, 32, 0, s>>>(w, mask, from_list, obs, init_only);
-    } else {
-        int grid = from_list ? 148 * 4 : min((w.E + 3) / 4, 148 * 8);
-        reset_philox_kernel<ObsT><<<grid, 128, 0, s>>>(w, mask, from_list, obs, init_only);
+        return cudaGetLastError();
     }
-    return cudaGetLastError();
+    switch (w.map_type) {
+        case T2D_MAP_MAZE: return launch_reset_map<ObsT, T2D_MAP_MAZE>(w, mask, from_list, obs, init_only, s);
+        case T2D_MAP_EMPTY: return launch_reset_map<ObsT, T2D_MAP_EMPTY>(w, mask, from_list, obs, init_only, s);
+        default: return launch_reset_map<ObsT, T2D_MAP_BLOCK>(w, mask, from_list, obs, init_only, s);
+    }
 }
 
 cudaError_t t2d_launch_reset_f32(const World &w, const uint8_t *mask, int from_list, float *obs, int init_only, cudaStream_t s) {

@@ -96,9 +96,11 @@ class Agent(object):
         else:
             host['actions'].copy_(actions32)  # D2H, synchronous
             self.env.step_host(host['actions'], host['obs'], host['reward'], host['done'])
-            self.obs_buf[t + 1].copy_(host['obs'], non_blocking=True)  # H2D from pinned memory
-            self.rew_buf[t].copy_(host['reward'], non_blocking=True)
-            self.done_buf[t].copy_(host['done'], non_blocking=True)
+            # H2D from pinned memory.  Through .data: the rollout slots share one allocation (one autograd version
+            # counter) and slot t is already saved for backward when slot t + 1 is filled.
+            self.obs_buf.data[t + 1].copy_(host['obs'], non_blocking=True)
+            self.rew_buf.data[t].copy_(host['reward'], non_blocking=True)
+            self.done_buf.data[t].copy_(host['done'], non_blocking=True)
         self.reward = self.rew_buf[t]
         self.done = self.done_buf[t]
         self.state = self.obs_buf[t + 1]
@@ -183,6 +185,6 @@ class Agent(object):
             allreduce(optimizer.fp.grad)
         optimizer.step(max_grad_norm=self.max_grad_norm, grad_scale=1.0 / world_size)
         self.clear_actions()
-        self.obs_buf[0].copy_(self.state)
+        self.obs_buf.data[0].copy_(self.state)
         self.state = self.obs_buf[0]
         return policy_loss.detach(), value_loss.detach(), entropies.detach().sum(0), pred_loss.detach()

@@ -82,7 +82,7 @@ def test_batched_learner_matches_oracle(env_id, network, aux, mode):
         dones = p.done_buf.cpu().numpy().astype(bool).copy()
         n_done += int(dones.sum())
         pl, vl, ent, prl = p.optimize(None, tr.optimizer, tr.model, mode, None, boot_forced_actions=torch.from_numpy(boot).cuda())
-        flat_grad = {n_: q.grad.detach().cpu().clone() for n_, q in tr.model.named_parameters()}
+        flat_grad = {n_: q.grad.detach().cpu().clone() for n_, q in tr.model.named_parameters() if q.grad is not None}
         mean_grad = {k: torch.zeros_like(v) for k, v in sd.items()}
         nhx, ncx = [], []
         for e in range(E):
