@@ -85,7 +85,7 @@ struct Philox {
         k1 = (uint32_t)(seed >> 32);
         c0 = env; c1 = episode; c2 = stream; blk = 0; have = 0;
     }
-    __device__ __noinline__ void block() {
+    __device__ __forceinline__ void block() {
         uint32_t x0 = c0, x1 = c1, x2 = c2, x3 = blk++;
         uint32_t a = k0, b = k1;
 #pragma unroll

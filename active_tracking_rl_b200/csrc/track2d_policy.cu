@@ -1,0 +1,313 @@
+// track2d_policy.cu -- the CNN_maze convolution stack (perception.py:68-92) as two fused fp32 kernels.
+//
+//   forward :  x [N][13][13] -> conv1 3x3/s2/p1 (1->16) -> ReLU -> conv2 3x3/s2/p1 (16->32) -> ReLU -> y2 [N][32*4*4]
+//   backward:  given dL/dy2, accumulates dW1, db1, dW2, db2 (the observation needs no gradient); the conv1
+//              activations are RECOMPUTED from x instead of being stored (7 k MAC per image vs 3 KB of HBM
+//              traffic each way), so nothing but x and y2 lives between forward and backward.
+//
+// N is (envs x frames): 65,536 tracker images + 131,072 target (TAT) images per env-step at the benchmark size,
+// i.e. a very tall, very thin problem (73.7 k MAC and ~2.7 KB per image).  cuDNN's fp32 kernels for these shapes run
+// at a few percent of the FP32 pipe (profiles/); here every CTA keeps both weight tensors and a group of 8 images
+// (zero-bordered, so no bounds tests) in shared memory and each thread owns a register tile:
+//   conv2 fwd   thread = (image, output position), 32 output-channel accumulators, weights via broadcast LDS.128
+//   dW2         thread = (4 output channels, 1 input channel), 36 accumulators that live across the whole grid-stride
+//               loop; one atomicAdd per weight per CTA at the end
+//   dy1         thread = (image, input channel), 49 accumulators with compile-time scatter indices
+// All arithmetic is fp32 FFMA, same operation set as the reference's float32 convs; summation order differs
+// (tolerance-level, tests/test_gpu_learner.py).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/track2d.h"
+
+void t2d_set_error(const char *fmt, ...);
+void t2d_count_launches(int n);
+
+namespace {
+
+constexpr int IMG = 8;          // images per CTA iteration
+constexpr int THREADS = 128;
+constexpr int XP = 15 * 15;     // zero-bordered input
+constexpr int Y1P = 81;         // zero-bordered 7x7 conv1 activation (9x9)
+
+struct ConvSmem {
+    float w2t[144 * 32];        // [ic*9+k][oc]   (forward, dW2)
+    float w1[16 * 9];
+    float b1[16];
+    float b2[32];
+    float xs[IMG][XP];
+    float y1[IMG][16][Y1P];
+};
+struct ConvBwdSmem {
+    ConvSmem f;
+    float w2[32 * 144];         // [oc][ic*9+k]   (dy1)
+    float dz2[IMG][16][32];     // [img][pos][oc]
+};
+
+__device__ __forceinline__ void load_weights(ConvSmem &s, const float *__restrict__ w1, const float *__restrict__ b1,
+                                             const float *__restrict__ w2, const float *__restrict__ b2, int tid) {
+    for (int i = tid; i < 32 * 144; i += THREADS) {
+        int oc = i / 144, r = i - oc * 144;
+        s.w2t[r * 32 + oc] = w2[i];
+    }
+    for (int i = tid; i < 144; i += THREADS) s.w1[i] = w1[i];
+    if (tid < 16) s.b1[tid] = b1[tid];
+    if (tid < 32) s.b2[tid] = b2 ? b2[tid] : 0.f;
+    // zero borders once: interiors are overwritten every iteration, borders never are
+    for (int i = tid; i < IMG * XP; i += THREADS) (&s.xs[0][0])[i] = 0.f;
+    for (int i = tid; i < IMG * 16 * Y1P; i += THREADS) (&s.y1[0][0][0])[i] = 0.f;
+}
+
+// stage IMG images and run conv1 + ReLU into the zero-bordered y1 tile.  thread = (image, channel)
+__device__ __forceinline__ void stage_and_conv1(ConvSmem &s, const float *__restrict__ x, int64_t n0, int nimg, int tid) {
+    for (int i = tid; i < IMG * 169; i += THREADS) {
+        int img = i / 169, c = i - img * 169;
+        int r = c / 13, q = c - r * 13;
+        s.xs[img][(r + 1) * 15 + q + 1] = img < nimg ? x[(n0 + img) * 169 + c] : 0.f;
+    }
+    __syncthreads();
+    const int img = tid >> 4, ch = tid & 15;
+    float w[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) w[k] = s.w1[ch * 9 + k];
+    const float b = s.b1[ch];
+    const float *xi = s.xs[img];
+    float *yo = s.y1[img][ch];
+#pragma unroll
+    for (int i = 0; i < 7; i++) {
+#pragma unroll
+        for (int j = 0; j < 7; j++) {
+            float a = b;
+#pragma unroll
+            for (int ki = 0; ki < 3; ki++)
+#pragma unroll
+                for (int kj = 0; kj < 3; kj++) a = fmaf(xi[(2 * i + ki) * 15 + 2 * j + kj], w[ki * 3 + kj], a);
+            yo[(i + 1) * 9 + j + 1] = fmaxf(a, 0.f);
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(THREADS) maze_conv_fwd_kernel(const float *__restrict__ x, int64_t N, const float *__restrict__ w1,
+                                                                const float *__restrict__ b1, const float *__restrict__ w2,
+                                                                const float *__restrict__ b2, float *__restrict__ y2) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ConvSmem &s = *reinterpret_cast<ConvSmem *>(smem_raw);
+    const int tid = threadIdx.x;
+    load_weights(s, w1, b1, w2, b2, tid);
+    __syncthreads();
+    const int img = tid >> 4, pos = tid & 15;
+    const int oi = pos >> 2, oj = pos & 3;
+    for (int64_t n0 = (int64_t)blockIdx.x * IMG; n0 < N; n0 += (int64_t)gridDim.x * IMG) {
+        const int nimg = (int)min((int64_t)IMG, N - n0);
+        stage_and_conv1(s, x, n0, nimg, tid);
+        float acc[32];
+#pragma unroll
+        for (int c = 0; c < 32; c++) acc[c] = s.b2[c];
+        const float *yi = &s.y1[img][0][(2 * oi) * 9 + 2 * oj];
+#pragma unroll 2
+        for (int ic = 0; ic < 16; ic++) {
+#pragma unroll
+            for (int k = 0; k < 9; k++) {
+                const float v = yi[ic * Y1P + (k / 3) * 9 + (k % 3)];
+                const float4 *wr = reinterpret_cast<const float4 *>(&s.w2t[(ic * 9 + k) * 32]);
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    float4 wv = wr[q];
+                    acc[4 * q + 0] = fmaf(v, wv.x, acc[4 * q + 0]);
+                    acc[4 * q + 1] = fmaf(v, wv.y, acc[4 * q + 1]);
+                    acc[4 * q + 2] = fmaf(v, wv.z, acc[4 * q + 2]);
+                    acc[4 * q + 3] = fmaf(v, wv.w, acc[4 * q + 3]);
+                }
+            }
+        }
+        if (img < nimg) {
+            float *o = y2 + (n0 + img) * 512 + pos;
+#pragma unroll
+            for (int c = 0; c < 32; c++) o[c * 16] = fmaxf(acc[c], 0.f);
+        }
+        __syncthreads(); // y1 / xs are rewritten by the next iteration
+    }
+}
+
+__global__ void __launch_bounds__(THREADS) maze_conv_bwd_kernel(const float *__restrict__ x, const float *__restrict__ y2,
+                                                                const float *__restrict__ gy2, int64_t N, const float *__restrict__ w1,
+                                                                const float *__restrict__ b1, const float *__restrict__ w2,
+                                                                float *__restrict__ dw1, float *__restrict__ db1, float *__restrict__ dw2,
+                                                                float *__restrict__ db2) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ConvBwdSmem &s = *reinterpret_cast<ConvBwdSmem *>(smem_raw);
+    const int tid = threadIdx.x;
+    load_weights(s.f, w1, b1, w2, nullptr, tid);
+    for (int i = tid; i < 32 * 144; i += THREADS) s.w2[i] = w2[i];
+    __syncthreads();
+
+    // persistent accumulators
+    const int ocg = tid & 7, icw = tid >> 3;    // dW2 tile: output channels 4*ocg..4*ocg+3, input channel icw
+    float aw2[4][9];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int k = 0; k < 9; k++) aw2[a][k] = 0.f;
+    const int img = tid >> 4, ic = tid & 15;    // dy1 / dW1 tile: (image, conv1 channel)
+    float aw1[9], ab1 = 0.f, ab2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 9; k++) aw1[k] = 0.f;
+
+    for (int64_t n0 = (int64_t)blockIdx.x * IMG; n0 < N; n0 += (int64_t)gridDim.x * IMG) {
+        const int nimg = (int)min((int64_t)IMG, N - n0);
+        stage_and_conv1(s.f, x, n0, nimg, tid);
+        // dz2 = dL/dy2 * (y2 > 0), transposed to [img][pos][oc]
+        {
+            const int oc = tid & 31, q4 = tid >> 5; // 4 warps: each takes positions q4*4 .. q4*4+3
+            for (int im = 0; im < IMG; im++) {
+#pragma unroll
+                for (int p = 0; p < 4; p++) {
+                    int pos = q4 * 4 + p;
+                    float d = 0.f;
+                    if (im < nimg) {
+                        int64_t gi = (n0 + im) * 512 + oc * 16 + pos;
+                        d = y2[gi] > 0.f ? gy2[gi] : 0.f;
+                    }
+                    s.dz2[im][pos][oc] = d;
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- dW2[oc][ic][k] += sum_{img,pos} dz2[img][pos][oc] * y1pad[img][ic][patch(pos, k)] ----------------
+        for (int im = 0; im < IMG; im++) {
+            const float *yi = s.f.y1[im][icw];
+#pragma unroll
+            for (int pos = 0; pos < 16; pos++) {
+                const float4 d = *reinterpret_cast<const float4 *>(&s.dz2[im][pos][ocg * 4]);
+                const int base = (2 * (pos >> 2)) * 9 + 2 * (pos & 3);
+#pragma unroll
+                for (int k = 0; k < 9; k++) {
+                    const float v = yi[base + (k / 3) * 9 + (k % 3)];
+                    aw2[0][k] = fmaf(d.x, v, aw2[0][k]);
+                    aw2[1][k] = fmaf(d.y, v, aw2[1][k]);
+                    aw2[2][k] = fmaf(d.z, v, aw2[2][k]);
+                    aw2[3][k] = fmaf(d.w, v, aw2[3][k]);
+                }
+            }
+        }
+        if (tid < 32) {
+            for (int im = 0; im < IMG; im++)
+#pragma unroll
+                for (int pos = 0; pos < 16; pos++) ab2 += s.dz2[im][pos][tid];
+        }
+
+        // ---- dy1[img][ic][7x7] = sum_{oc,pos,k} dz2[img][pos][oc] * w2[oc][ic][k]; then dz1 = dy1 * (y1 > 0) ------
+        float dy[49];
+#pragma unroll
+        for (int p = 0; p < 49; p++) dy[p] = 0.f;
+        for (int oc = 0; oc < 32; oc++) {
+            float w[9];
+#pragma unroll
+            for (int k = 0; k < 9; k++) w[k] = s.w2[oc * 144 + ic * 9 + k];
+#pragma unroll
+            for (int pos = 0; pos < 16; pos++) {
+                const float d = s.dz2[img][pos][oc];
+#pragma unroll
+                for (int ki = 0; ki < 3; ki++)
+#pragma unroll
+                    for (int kj = 0; kj < 3; kj++) {
+                        const int r = 2 * (pos >> 2) + ki - 1, c = 2 * (pos & 3) + kj - 1; // compile-time after unrolling
+                        if (r >= 0 && r < 7 && c >= 0 && c < 7) dy[r * 7 + c] = fmaf(d, w[ki * 3 + kj], dy[r * 7 + c]);
+                    }
+            }
+        }
+        // ---- dW1[ch][k] += sum dz1 * xpad ; db1 ----------------------------------------------------------------
+        {
+            const float *yi = s.f.y1[img][ic];
+            const float *xi = s.f.xs[img];
+#pragma unroll
+            for (int i = 0; i < 7; i++)
+#pragma unroll
+                for (int j = 0; j < 7; j++) {
+                    const float dz = yi[(i + 1) * 9 + j + 1] > 0.f ? dy[i * 7 + j] : 0.f;
+                    ab1 += dz;
+#pragma unroll
+                    for (int ki = 0; ki < 3; ki++)
+#pragma unroll
+                        for (int kj = 0; kj < 3; kj++) aw1[ki * 3 + kj] = fmaf(dz, xi[(2 * i + ki) * 15 + 2 * j + kj], aw1[ki * 3 + kj]);
+                }
+        }
+        __syncthreads();
+    }
+
+    // ---- flush the persistent accumulators ------------------------------------------------------------------
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int k = 0; k < 9; k++) atomicAdd(&dw2[(ocg * 4 + a) * 144 + icw * 9 + k], aw2[a][k]);
+    if (tid < 32) atomicAdd(&db2[tid], ab2);
+    // dW1 / db1: 8 threads (one per image slot) share a channel: reduce through shared memory first
+    float *red = reinterpret_cast<float *>(&s.dz2[0][0][0]);
+    __syncthreads();
+    for (int i = tid; i < 16 * 10; i += THREADS) red[i] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 9; k++) atomicAdd(&red[ic * 10 + k], aw1[k]);
+    atomicAdd(&red[ic * 10 + 9], ab1);
+    __syncthreads();
+    if (tid < 16 * 9) atomicAdd(&dw1[tid], red[(tid / 9) * 10 + tid % 9]);
+    if (tid < 16) atomicAdd(&db1[tid], red[tid * 10 + 9]);
+}
+
+int grid_for(int64_t N, int ctas_per_sm) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int64_t groups = (N + IMG - 1) / IMG;
+    int64_t g = (int64_t)sms * ctas_per_sm;
+    return (int)(groups < g ? groups : g);
+}
+
+} // namespace
+
+extern "C" int track2d_maze_conv_forward(const float *x, int64_t n_images, const float *w1, const float *b1, const float *w2,
+                                         const float *b2, float *y2, void *stream) {
+    if (!x || !w1 || !b1 || !w2 || !b2 || !y2 || n_images < 1) {
+        t2d_set_error("track2d_maze_conv_forward: bad argument");
+        return T2D_E_INVALID;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(maze_conv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ConvSmem));
+        cudaFuncSetAttribute(maze_conv_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ConvBwdSmem));
+        attr_set = true;
+    }
+    t2d_count_launches(1);
+    maze_conv_fwd_kernel<<<grid_for(n_images, 3), THREADS, sizeof(ConvSmem), (cudaStream_t)stream>>>(x, n_images, w1, b1, w2, b2, y2);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) {
+        t2d_set_error("track2d_maze_conv_forward: %s", cudaGetErrorString(err));
+        return T2D_E_CUDA;
+    }
+    return T2D_OK;
+}
+
+extern "C" int track2d_maze_conv_backward(const float *x, const float *y2, const float *gy2, int64_t n_images, const float *w1,
+                                          const float *b1, const float *w2, float *dw1, float *db1, float *dw2, float *db2, void *stream) {
+    if (!x || !y2 || !gy2 || !w1 || !b1 || !w2 || !dw1 || !db1 || !dw2 || !db2 || n_images < 1) {
+        t2d_set_error("track2d_maze_conv_backward: bad argument");
+        return T2D_E_INVALID;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(maze_conv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ConvSmem));
+        cudaFuncSetAttribute(maze_conv_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ConvBwdSmem));
+        attr_set = true;
+    }
+    t2d_count_launches(1);
+    maze_conv_bwd_kernel<<<grid_for(n_images, 2), THREADS, sizeof(ConvBwdSmem), (cudaStream_t)stream>>>(x, y2, gy2, n_images, w1, b1, w2, dw1, db1,
+                                                                                                        dw2, db2);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) {
+        t2d_set_error("track2d_maze_conv_backward: %s", cudaGetErrorString(err));
+        return T2D_E_CUDA;
+    }
+    return T2D_OK;
+}

@@ -18,6 +18,87 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 
+class _Conv3x3S2(torch.autograd.Function):
+    """3x3 / stride 2 / pad 1 convolution (perception.py:71-72) with a GEMM-shaped backward.
+
+    cuDNN's fp32 backward kernels for these shapes (1->16 and 16->32 channels on 13x13 / 7x7 images, a few hundred
+    thousand images per call) run at a few percent of the machine (dgrad2d_grouped_direct 14.8 ms, wgrad_alg1 5 ms
+    per call at 196,608 images; profiles/).  Here the backward recomputes the im2col matrix directly in
+    [C*9, N*L] layout (one gather), and both gradients are plain SGEMMs with a long reduction axis:
+        dW [OC, C*9]   = dY [OC, N*L] @ cols^T
+        dcols [C*9, N*L] = W^T @ dY, scattered back with 9 strided adds (col2im)
+    Nothing but x and w is kept between forward and backward."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        ctx.save_for_backward(x, w)
+        return F.conv2d(x, w, b, stride=2, padding=1)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        N, C, H, W = x.shape
+        OC, OH, OW = w.shape[0], gy.shape[2], gy.shape[3]
+        K, NL = C * 9, N * OH * OW
+        g = gy.permute(1, 0, 2, 3).reshape(OC, NL)  # [OC, N*L]
+        gb = g.sum(1)
+        xp = F.pad(x, (1, 1, 1, 1))
+        win = xp.unfold(2, 3, 2).unfold(3, 3, 2)  # [N, C, OH, OW, 3, 3] view
+        cols = win.permute(1, 4, 5, 0, 2, 3).reshape(K, NL)  # one gather, [C*9, N*L]
+        gw = torch.mm(g, cols.t()).view_as(w)
+        gx = None
+        if ctx.needs_input_grad[0]:
+            dcols = torch.mm(w.view(OC, K).t(), g).view(C, 3, 3, N, OH, OW)
+            gxp = x.new_zeros((C, N, H + 2, W + 2))
+            for ki in range(3):
+                for kj in range(3):
+                    gxp[:, :, ki:ki + 2 * OH:2, kj:kj + 2 * OW:2] += dcols[:, ki, kj]
+            gx = gxp[:, :, 1:H + 1, 1:W + 1].permute(1, 0, 2, 3)
+        return gx, gw, gb
+
+
+def conv3x3s2(x, conv):
+    return _Conv3x3S2.apply(x, conv.weight, conv.bias)
+
+
+class _MazeConvStack(torch.autograd.Function):
+    """conv1 + ReLU + conv2 + ReLU of CNN_maze as ONE hand-written CUDA kernel each way (csrc/track2d_policy.cu,
+    track2d_maze_conv_forward / _backward).  x (N, 1, 13, 13) -> (N, 512)."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2):
+        import ctypes as C
+        from . import _lib
+        lib = _lib.load()
+        x = x.contiguous()
+        N = x.shape[0]
+        y2 = torch.empty((N, 512), dtype=torch.float32, device=x.device)
+        p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+        _lib.check(lib.track2d_maze_conv_forward(p(x), N, p(w1), p(b1), p(w2), p(b2), p(y2),
+                                                 C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)), lib)
+        ctx.save_for_backward(x, y2, w1, b1, w2)
+        return y2
+
+    @staticmethod
+    def backward(ctx, gy2):
+        import ctypes as C
+        from . import _lib
+        lib = _lib.load()
+        x, y2, w1, b1, w2 = ctx.saved_tensors
+        gy2 = gy2.contiguous()
+        dw1, db1, dw2 = torch.zeros_like(w1), torch.zeros_like(b1), torch.zeros_like(w2)
+        db2 = torch.zeros(32, dtype=torch.float32, device=x.device)
+        p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+        _lib.check(lib.track2d_maze_conv_backward(p(x), p(y2), p(gy2), x.shape[0], p(w1), p(b1), p(w2), p(dw1), p(db1), p(dw2), p(db2),
+                                                  C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)), lib)
+        return None, dw1, db1, dw2, db2
+
+
+# "fused": the hand-written conv-stack kernels (CUDA tensors); "gemm_backward": cuDNN forward + im2col/SGEMM backward;
+# "cudnn": plain F.conv2d autograd.  CPU tensors (tests of the host-side logic) always take the F.conv2d route.
+CONV_IMPL = "fused"
+
+
 def weights_init(m):
     """utils.py:47-62: U(+-sqrt(6 / (fan_in + fan_out))) for every Conv / Linear, zero bias.  It is the
     LAST init applied (model.py:130,187 `self.apply(weights_init)`), so it overrides norm_col_init etc."""
@@ -55,8 +136,14 @@ class CNN_maze(nn.Module):
         """x: (B, frames, C, H, W) -> (B, 256)"""
         B = x.shape[0]
         y = x.reshape((B * self.frames,) + tuple(x.shape[2:]))
-        y = F.relu(self.conv1(y))
-        y = F.relu(self.conv2(y))
+        if CONV_IMPL == "fused" and y.is_cuda and y.shape[1:] == (1, 13, 13) and not y.requires_grad:
+            y = _MazeConvStack.apply(y, self.conv1.weight, self.conv1.bias, self.conv2.weight, self.conv2.bias)
+        elif CONV_IMPL == "gemm_backward":
+            y = F.relu(conv3x3s2(y, self.conv1))
+            y = F.relu(conv3x3s2(y, self.conv2))
+        else:
+            y = F.relu(self.conv1(y))
+            y = F.relu(self.conv2(y))
         return F.relu(self.fc(y.reshape(B, -1)))
 
 

@@ -178,6 +178,17 @@ int track2d_sharedadam_step(float *param_dev, const float *grad_dev, float *exp_
 int track2d_gae_returns(const float *rewards_dev, const uint8_t *done_dev, const float *values_dev, float *returns_dev,
                         float *gae_dev, int32_t T, int64_t E, double gamma, double tau, void *stream);
 
+/* CNN_maze's convolution stack (perception.py:71-72,86-88) fused: conv1 3x3/s2/p1 (1->16) + ReLU + conv2 3x3/s2/p1
+ * (16->32) + ReLU.  x [n_images][13][13] float32 -> y2 [n_images][512] in (channel, row, col) order, i.e. what
+ * `x.view(1, -1)` (perception.py:89) flattens.  Device pointers; w1 [16][1][3][3], w2 [32][16][3][3]. */
+int track2d_maze_conv_forward(const float *x_dev, int64_t n_images, const float *w1_dev, const float *b1_dev, const float *w2_dev,
+                              const float *b2_dev, float *y2_dev, void *stream);
+/* its backward: given gy2 = dL/dy2, ACCUMULATES (+=) dL/dw1, db1, dw2, db2 into the given buffers (zero them first for a
+ * fresh gradient).  The conv1 activations are recomputed from x; the observation gets no gradient. */
+int track2d_maze_conv_backward(const float *x_dev, const float *y2_dev, const float *gy2_dev, int64_t n_images, const float *w1_dev,
+                               const float *b1_dev, const float *w2_dev, float *dw1_dev, float *db1_dev, float *dw2_dev, float *db2_dev,
+                               void *stream);
+
 #ifdef __cplusplus
 }
 #endif

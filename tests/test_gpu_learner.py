@@ -153,3 +153,27 @@ def test_training_runs_and_improves_value_loss():
     assert last < first, (first, last)
     assert tr.env.status() == 0
     tr.env.close()
+
+
+@pytest.mark.parametrize("N", [1, 7, 8, 1000, 5003])
+def test_fused_conv_stack_matches_torch(N):
+    """csrc/track2d_policy.cu vs F.conv2d in float64: forward 1e-5, weight gradients 1e-4 relative (fp32 sums over N)."""
+    import torch.nn.functional as F
+    from active_tracking_rl_b200.model import _MazeConvStack
+    g = torch.Generator(device="cuda").manual_seed(N)
+    x = torch.randint(0, 5, (N, 1, 13, 13), generator=g, device="cuda").float()
+    w1 = (torch.rand(16, 1, 3, 3, generator=g, device="cuda") - 0.5).requires_grad_(True)
+    b1 = (torch.rand(16, generator=g, device="cuda") - 0.5).requires_grad_(True)
+    w2 = ((torch.rand(32, 16, 3, 3, generator=g, device="cuda") - 0.5) * 0.3).requires_grad_(True)
+    b2 = (torch.rand(32, generator=g, device="cuda") - 0.5).requires_grad_(True)
+    gy = torch.randn(N, 512, generator=g, device="cuda")
+    y = _MazeConvStack.apply(x, w1, b1, w2, b2)
+    grads = torch.autograd.grad(y, [w1, b1, w2, b2], gy)
+    d = lambda t: t.detach().double()  # noqa: E731
+    W1, B1, W2, B2 = [d(t).requires_grad_(True) for t in (w1, b1, w2, b2)]
+    yr = F.relu(F.conv2d(F.relu(F.conv2d(x.double(), W1, B1, stride=2, padding=1)), W2, B2, stride=2, padding=1)).reshape(N, 512)
+    gr = torch.autograd.grad(yr, [W1, B1, W2, B2], gy.double())
+    assert torch.allclose(y.double(), yr, rtol=1e-5, atol=1e-5), (y.double() - yr).abs().max()
+    for a, b, name in zip(grads, gr, ("w1", "b1", "w2", "b2")):
+        scale = float(b.abs().max()) + 1e-6
+        assert float((a.double() - b).abs().max()) <= 1e-4 * scale + 1e-5, (name, float((a.double() - b).abs().max()), scale)
