@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(THREADS) maze_conv_bwd_kernel(const float *__r
     for (int k = 0; k < 9; k++) atomicAdd(&red[ic * 10 + k], aw1[k]);
     atomicAdd(&red[ic * 10 + 9], ab1);
     __syncthreads();
-    if (tid < 16 * 9) atomicAdd(&dw1[tid], red[(tid / 9) * 10 + tid % 9]);
+    for (int i = tid; i < 16 * 9; i += THREADS) atomicAdd(&dw1[i], red[(i / 9) * 10 + i % 9]);
     if (tid < 16) atomicAdd(&db1[tid], red[tid * 10 + 9]);
 }
 
