@@ -318,7 +318,10 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--traffic-bytes", type=float, default=None, help="dram bytes per step-kernel launch from the committed ncu capture")
+    ap.add_argument("--traffic-bytes", type=float, default=60907008.0,
+                    help="dram__bytes_read.sum + dram__bytes_write.sum per step-kernel launch from the committed ncu capture "
+                         "(profiles/ncu_r1_kernels.txt: 27.46 MB read + 33.44 MB written INSIDE the kernel; the 126 MB write-back L2 "
+                         "retires the rest of the 88.6 MB of observations after the kernel ends)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
     if a.impl == "reference":

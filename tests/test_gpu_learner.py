@@ -177,3 +177,30 @@ def test_fused_conv_stack_matches_torch(N):
     for a, b, name in zip(grads, gr, ("w1", "b1", "w2", "b2")):
         scale = float(b.abs().max()) + 1e-6
         assert float((a.double() - b).abs().max()) <= 1e-4 * scale + 1e-5, (name, float((a.double() - b).abs().max()), scale)
+
+
+def test_evaluator_statistics_and_checkpoints(tmp_path):
+    """gym_eval.py / test.py equivalents: statistics layout, CSV header, reference-format checkpoints."""
+    import csv
+    import os
+    from active_tracking_rl_b200 import gym_eval
+    from active_tracking_rl_b200.train import Trainer, default_args
+    args = default_args(num_envs=256, seed=2, test_eps=64, env_base="Track2D-BlockPartialRam-v0", split=True)
+    tr = Trainer(args, "cuda:0")
+    stats = gym_eval.evaluate(tr.model, "Track2D-BlockPartialRam-v0", 64, seed=5)
+    assert 11 <= stats["EL_mean"] <= 500 and 0.0 <= stats["S_rate"] <= 1.0 and stats["R_std"] >= 0
+    path = os.path.join(tmp_path, "r.csv")
+    gym_eval.write_csv(path, stats)
+    gym_eval.write_csv(path, stats)
+    rows = list(csv.reader(open(path)))
+    assert rows[0] == gym_eval.HEADER and len(rows) == 3
+    # same seed, same statistics (device RNG is counter-based)
+    again = gym_eval.evaluate(tr.model, "Track2D-BlockPartialRam-v0", 64, seed=5)
+    assert again["EL_mean"] == stats["EL_mean"] and abs(again["R_mean"] - stats["R_mean"]) < 1e-9
+    ev = gym_eval.Evaluator(args, str(tmp_path))
+    out = ev.run(tr.model, n_iter=7)
+    assert out["checkpoint"] == "all-best-7.dat" and os.path.exists(os.path.join(tmp_path, "tracker-best.dat"))
+    sd = torch.load(os.path.join(tmp_path, "all-best-7.dat"))
+    assert list(sd.keys()) == list(a3c_oracle.det_state_dict(tat=True).keys())
+    gym_eval.load_weights(tr.model, load_tracker=os.path.join(tmp_path, "tracker-best.dat"), load_target=os.path.join(tmp_path, "target-best.dat"))
+    tr.env.close()

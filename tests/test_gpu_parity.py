@@ -400,3 +400,65 @@ def test_sharedadam_kernel_matches_reference_formula(t2d):
         pr = pr - step_size * mr / (xr.sqrt() + eps)
         assert torch.allclose(p.double(), pr, rtol=0, atol=5e-6), (step, (p.double() - pr).abs().max())  # fp32 state vs fp64 restatement
         assert torch.allclose(vmax.double(), xr, rtol=1e-5, atol=1e-9)
+
+
+def _bfs_dist(maze, start, goal):
+    from collections import deque
+    H, W = maze.shape
+    dist = -np.ones((H, W), np.int32)
+    dist[start[0], start[1]] = 0
+    q = deque([tuple(start)])
+    while q:
+        r, c = q.popleft()
+        if (r, c) == tuple(goal):
+            return int(dist[r, c])
+        for dr, dc in ((-1, 0), (1, 0), (0, -1), (0, 1)):
+            nr, nc = r + dr, c + dc
+            if maze[nr, nc] == 0 and dist[nr, nc] < 0:
+                dist[nr, nc] = dist[r, c] + 1
+                q.append((nr, nc))
+    return -1
+
+
+@pytest.mark.parametrize("env_id", ["Track2D-BlockPartialNav-v0", "Track2D-MazePartialNav-v0"])
+def test_philox_navigator_plans_are_valid_shortest_paths(t2d, env_id):
+    """Philox mode has no reference stream to match; the Navigator's contract is checked instead: every plan is a
+    wall-free path from the target to its goal of BFS-optimal length (A* with an admissible heuristic), and the
+    target executes it action by action, replanning when it runs out (navigator.py:11-36)."""
+    E = 96
+    env = t2d.Track2DVecEnv(env_id, num_envs=E, seed=21, rng="philox", auto_reset=True)
+    env.reset()
+    D = {0: (-1, 0), 1: (1, 0), 2: (0, -1), 3: (0, 1)}
+
+    def check_plans(envs):
+        maps, (pos, _), (plan, ln, idx, goal) = env.get_maps(), env.get_agents(), env.get_nav()
+        for e in envs:
+            if ln[e] == 10 and _bfs_dist(maps[e], pos[e, 1], goal[e]) != 10:
+                continue  # plan B (10 random actions) after 6 failed goals: astronomically rare, but legal
+            r, c = pos[e, 1]
+            for a in plan[e, idx[e]:ln[e]]:
+                r, c = r + D[int(a)][0], c + D[int(a)][1]
+                assert maps[e, r, c] == 0, "plan walks into a wall"
+            assert (r, c) == tuple(goal[e])
+            if idx[e] == 0:
+                assert ln[e] == _bfs_dist(maps[e], pos[e, 1], goal[e]), "A* plan is not a shortest path"
+    check_plans(range(E))
+    g = torch.Generator(device="cuda").manual_seed(3)
+    replans = 0
+    for t in range(120):
+        pos, _ = env.get_agents()
+        d = pos[:, 1] - pos[:, 0]  # tracker chases the target so episodes live long enough to exhaust plans
+        a0 = np.where(np.abs(d[:, 0]) >= np.abs(d[:, 1]), np.where(d[:, 0] < 0, 0, 1), np.where(d[:, 1] < 0, 2, 3))
+        acts = torch.from_numpy(np.stack([a0, np.zeros(E, np.int64)], 1).astype(np.int32)).cuda()
+        plan, ln, idx, goal = env.get_nav()
+        env.step(acts)
+        tgt = env.get_target_actions()
+        cont = idx < ln  # no replan needed before this step: the executed action is the planned one
+        assert (tgt[cont] == plan[np.arange(E), np.minimum(idx, 1023)][cont]).all()
+        replans += int((~cont).sum())
+        if t % 40 == 39:
+            _, ln2, idx2, _ = env.get_nav()
+            check_plans(np.nonzero(idx2 < ln2)[0][:24])
+    assert replans > 0, "no plan ran out: the replan kernel was not exercised"
+    assert env.status() == 0
+    env.close()
