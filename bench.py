@@ -291,7 +291,13 @@ def run_gpu_arm(a):
            "ms_per_step": ms2, "steps": k2,
            "what": "Agent.action_train with env.step via track2d_step_host (pinned host buffers) and the observation re-uploaded, per GPU"}
     status = tr.env.status()
-    if world > 1:
+    replicas_identical = None
+    if world > 1:  # every rank applied the same fused update to the same all-reduced gradient: the weights must be bit-identical
+        chk = tr.optimizer.fp.flat.double().sum().reshape(1)
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        replicas_identical = bool((lo == hi).item())
         dist.destroy_process_group()
     if rank != 0:
         return
@@ -303,7 +309,7 @@ def run_gpu_arm(a):
                    "rng": "philox", "l2": "rollout observation buffers (21 x %.0f MB) and the roofline ring exceed the 126 MB L2" % (obs_b / 1e6),
                    "policy_math": "float32 (TF32 off)", "max_grad_norm": args.max_grad_norm},
         "roofline": roofline, "env_only": env_only, "cpu_baseline": cpu_base, "e2e": e2e, "clocks": clocks,
-        "gpu_launches": int(launches), "device_status": status,
+        "gpu_launches": int(launches), "device_status": status, "replicas_identical": replicas_identical,
     }
     print(json.dumps(line), flush=True)
 
