@@ -96,35 +96,47 @@ __global__ void __launch_bounds__(THREADS) maze_conv_fwd_kernel(const float *__r
     const int tid = threadIdx.x;
     load_weights(s, w1, b1, w2, b2, tid);
     __syncthreads();
-    const int img = tid >> 4, pos = tid & 15;
-    const int oi = pos >> 2, oj = pos & 3;
+    // thread = (image, pair of horizontally adjacent output positions, half of the output channels): 2 x 16 accumulators.
+    // Per (ic, k) that is 4 LDS.128 of weights + (shared) activations for 32 FMAs -- 6 shared-memory wavefronts per
+    // 32 FMA cycles, so the FMA pipe, not the LSU, is the limiter (the 1 x 32 tiling needed 10 per 32).
+    const int img = tid >> 4, sub = tid & 15, pp = sub & 7, och = sub >> 3;
+    const int oi = pp >> 1, oj0 = (pp & 1) * 2;
     for (int64_t n0 = (int64_t)blockIdx.x * IMG; n0 < N; n0 += (int64_t)gridDim.x * IMG) {
         const int nimg = (int)min((int64_t)IMG, N - n0);
         stage_and_conv1(s, x, n0, nimg, tid);
-        float acc[32];
+        float accA[16], accB[16];
 #pragma unroll
-        for (int c = 0; c < 32; c++) acc[c] = s.b2[c];
-        const float *yi = &s.y1[img][0][(2 * oi) * 9 + 2 * oj];
+        for (int c = 0; c < 16; c++) accA[c] = accB[c] = s.b2[och * 16 + c];
+        const float *yi = &s.y1[img][0][(2 * oi) * 9 + 2 * oj0];
 #pragma unroll 2
         for (int ic = 0; ic < 16; ic++) {
+            float v[3][5];
+#pragma unroll
+            for (int ki = 0; ki < 3; ki++)
+#pragma unroll
+                for (int cj = 0; cj < 5; cj++) v[ki][cj] = yi[ic * Y1P + ki * 9 + cj];
 #pragma unroll
             for (int k = 0; k < 9; k++) {
-                const float v = yi[ic * Y1P + (k / 3) * 9 + (k % 3)];
-                const float4 *wr = reinterpret_cast<const float4 *>(&s.w2t[(ic * 9 + k) * 32]);
+                const float4 *wr = reinterpret_cast<const float4 *>(&s.w2t[(ic * 9 + k) * 32 + och * 16]);
+                const float va = v[k / 3][k % 3], vb = v[k / 3][k % 3 + 2];
 #pragma unroll
-                for (int q = 0; q < 8; q++) {
-                    float4 wv = wr[q];
-                    acc[4 * q + 0] = fmaf(v, wv.x, acc[4 * q + 0]);
-                    acc[4 * q + 1] = fmaf(v, wv.y, acc[4 * q + 1]);
-                    acc[4 * q + 2] = fmaf(v, wv.z, acc[4 * q + 2]);
-                    acc[4 * q + 3] = fmaf(v, wv.w, acc[4 * q + 3]);
+                for (int q = 0; q < 4; q++) {
+                    const float4 wv = wr[q];
+                    accA[4 * q + 0] = fmaf(va, wv.x, accA[4 * q + 0]);
+                    accA[4 * q + 1] = fmaf(va, wv.y, accA[4 * q + 1]);
+                    accA[4 * q + 2] = fmaf(va, wv.z, accA[4 * q + 2]);
+                    accA[4 * q + 3] = fmaf(va, wv.w, accA[4 * q + 3]);
+                    accB[4 * q + 0] = fmaf(vb, wv.x, accB[4 * q + 0]);
+                    accB[4 * q + 1] = fmaf(vb, wv.y, accB[4 * q + 1]);
+                    accB[4 * q + 2] = fmaf(vb, wv.z, accB[4 * q + 2]);
+                    accB[4 * q + 3] = fmaf(vb, wv.w, accB[4 * q + 3]);
                 }
             }
         }
         if (img < nimg) {
-            float *o = y2 + (n0 + img) * 512 + pos;
+            float *o = y2 + (n0 + img) * 512 + (och * 16) * 16 + oi * 4 + oj0;
 #pragma unroll
-            for (int c = 0; c < 32; c++) o[c * 16] = fmaxf(acc[c], 0.f);
+            for (int c = 0; c < 16; c++) *reinterpret_cast<float2 *>(o + c * 16) = make_float2(fmaxf(accA[c], 0.f), fmaxf(accB[c], 0.f));
         }
         __syncthreads(); // y1 / xs are rewritten by the next iteration
     }
@@ -179,16 +191,22 @@ __global__ void __launch_bounds__(THREADS) maze_conv_bwd_kernel(const float *__r
         for (int im = 0; im < IMG; im++) {
             const float *yi = s.f.y1[im][icw];
 #pragma unroll
-            for (int pos = 0; pos < 16; pos++) {
-                const float4 d = *reinterpret_cast<const float4 *>(&s.dz2[im][pos][ocg * 4]);
-                const int base = (2 * (pos >> 2)) * 9 + 2 * (pos & 3);
+            for (int pr = 0; pr < 8; pr++) { // pairs of horizontally adjacent output positions share 3 x 5 activations
+                const int oi = pr >> 1, oj0 = (pr & 1) * 2;
+                const float4 dA = *reinterpret_cast<const float4 *>(&s.dz2[im][oi * 4 + oj0][ocg * 4]);
+                const float4 dB = *reinterpret_cast<const float4 *>(&s.dz2[im][oi * 4 + oj0 + 1][ocg * 4]);
+                float v[3][5];
+#pragma unroll
+                for (int ki = 0; ki < 3; ki++)
+#pragma unroll
+                    for (int cj = 0; cj < 5; cj++) v[ki][cj] = yi[(2 * oi + ki) * 9 + 2 * oj0 + cj];
 #pragma unroll
                 for (int k = 0; k < 9; k++) {
-                    const float v = yi[base + (k / 3) * 9 + (k % 3)];
-                    aw2[0][k] = fmaf(d.x, v, aw2[0][k]);
-                    aw2[1][k] = fmaf(d.y, v, aw2[1][k]);
-                    aw2[2][k] = fmaf(d.z, v, aw2[2][k]);
-                    aw2[3][k] = fmaf(d.w, v, aw2[3][k]);
+                    const float va = v[k / 3][k % 3], vb = v[k / 3][k % 3 + 2];
+                    aw2[0][k] = fmaf(dB.x, vb, fmaf(dA.x, va, aw2[0][k]));
+                    aw2[1][k] = fmaf(dB.y, vb, fmaf(dA.y, va, aw2[1][k]));
+                    aw2[2][k] = fmaf(dB.z, vb, fmaf(dA.z, va, aw2[2][k]));
+                    aw2[3][k] = fmaf(dB.w, vb, fmaf(dA.w, va, aw2[3][k]));
                 }
             }
         }
