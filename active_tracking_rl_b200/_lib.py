@@ -67,7 +67,7 @@ SYMBOLS = {
     "track2d_maze_conv_forward": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "track2d_maze_conv_backward": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "track2d_gae_returns": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i64, _dbl, _dbl, _vp]),
-    "track2d_sharedadam_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _dbl, _dbl, _dbl, _dbl, _dbl, _dbl, _vp, _vp]),
+    "track2d_sharedadam_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _dbl, _dbl, _dbl, _dbl, _dbl, _dbl, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -39,6 +39,17 @@ __global__ void __launch_bounds__(256) sqnorm_kernel(const float *__restrict__ g
     }
 }
 
+// CUDA-graph-safe update counter: the count lives in device memory and the bias-corrected step size
+// (shared_optim.py:169-173, python floats = double) is derived from it on the device
+__global__ void adam_prep_kernel(long long *step_dev, float *neg_step_out, double lr, double beta1, double beta2) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        long long t = *step_dev + 1;
+        *step_dev = t;
+        double bc1 = 1.0 - pow(beta1, (double)t), bc2 = 1.0 - pow(beta2, (double)t);
+        *neg_step_out = (float)(-(lr * sqrt(bc2) / bc1));
+    }
+}
+
 __device__ __forceinline__ void adam_one(float &p, float g, float &m, float &v, float &vmax, float b1, float b2, float eps, float neg_step) {
     m = m * b1 + (1.f - b1) * g;
     v = v * b2 + (1.f - b2) * g * g;
@@ -50,7 +61,8 @@ __device__ __forceinline__ void adam_one(float &p, float g, float &m, float &v, 
 __global__ void __launch_bounds__(256) sharedadam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m,
                                                          float *__restrict__ v, float *__restrict__ vmax, int64_t n, float b1, float b2,
                                                          float eps, float neg_step, float max_norm, float grad_scale,
-                                                         const float *__restrict__ sqnorm) {
+                                                         const float *__restrict__ sqnorm, const float *__restrict__ neg_step_dev) {
+    if (neg_step_dev) neg_step = *neg_step_dev;
     // clip_grad_norm_: coef = max_norm / (total_norm + 1e-6), clamped to <= 1
     float coef = grad_scale;
     if (max_norm > 0.f) {
@@ -111,8 +123,9 @@ void t2d_count_launches(int n);
 
 extern "C" int track2d_sharedadam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, float *max_exp_avg_sq,
                                        int64_t n, int64_t step, double lr, double beta1, double beta2, double eps, double max_grad_norm,
-                                       double grad_scale, float *norm_scratch, void *stream) {
-    if (!param || !grad || !exp_avg || !exp_avg_sq || !max_exp_avg_sq || n <= 0 || step < 1 || (max_grad_norm > 0.f && !norm_scratch)) {
+                                       double grad_scale, float *norm_scratch, int64_t *step_dev, void *stream) {
+    if (!param || !grad || !exp_avg || !exp_avg_sq || !max_exp_avg_sq || n <= 0 || (!step_dev && step < 1) ||
+        ((max_grad_norm > 0.0 || step_dev) && !norm_scratch)) {
         t2d_set_error("track2d_sharedadam_step: bad argument");
         return T2D_E_INVALID;
     }
@@ -121,7 +134,7 @@ extern "C" int track2d_sharedadam_step(float *param, const float *grad, float *e
         return T2D_E_INVALID;
     }
     cudaStream_t s = (cudaStream_t)stream;
-    t2d_count_launches(max_grad_norm > 0.0 ? 2 : 1);
+    t2d_count_launches((max_grad_norm > 0.0 ? 2 : 1) + (step_dev ? 1 : 0));
     int grid = (int)((n / 4 + 255) / 256);
     if (grid < 1) grid = 1;
     if (grid > 148 * 8) grid = 148 * 8;
@@ -130,10 +143,17 @@ extern "C" int track2d_sharedadam_step(float *param, const float *grad, float *e
         sqnorm_kernel<<<grid, 256, 0, s>>>(grad, n, (float)grad_scale, norm_scratch);
     }
     // shared_optim.py:169-173 (python floats = double)
-    double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
-    float neg_step = (float)(-(lr * sqrt(bc2) / bc1));
+    float neg_step = 0.f;
+    const float *neg_step_dev = nullptr;
+    if (step_dev) {
+        adam_prep_kernel<<<1, 32, 0, s>>>(reinterpret_cast<long long *>(step_dev), norm_scratch + 1, lr, beta1, beta2);
+        neg_step_dev = norm_scratch + 1;
+    } else {
+        double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+        neg_step = (float)(-(lr * sqrt(bc2) / bc1));
+    }
     sharedadam_kernel<<<grid, 256, 0, s>>>(param, grad, exp_avg, exp_avg_sq, max_exp_avg_sq, n, (float)beta1, (float)beta2, (float)eps,
-                                            neg_step, (float)max_grad_norm, (float)grad_scale, norm_scratch);
+                                            neg_step, (float)max_grad_norm, (float)grad_scale, norm_scratch, neg_step_dev);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) {
         t2d_set_error("track2d_sharedadam_step: %s", cudaGetErrorString(err));

@@ -37,8 +37,13 @@ class Agent(object):
         self.done = None
         self.reward = None
         self.info = None
-        self.hxs = torch.zeros(self.num_envs, self.num_agents, self.rnn_out, device=self.device)
-        self.cxs = torch.zeros(self.num_envs, self.num_agents, self.rnn_out, device=self.device)
+        # persistent recurrent-state storage: a rollout starts from it and writes its final state back in place, so the
+        # whole iteration reads and writes fixed addresses (needed for CUDA-graph replay, harmless otherwise)
+        self.hx_store = torch.zeros(self.num_envs, self.num_agents, self.rnn_out, device=self.device)
+        self.cx_store = torch.zeros(self.num_envs, self.num_agents, self.rnn_out, device=self.device)
+        self.hxs, self.cxs = self.hx_store, self.cx_store
+        self._w_ent_key = (float(args.entropy), float(self.w_entropy_target))
+        self.w_ent = torch.tensor(list(self._w_ent_key), device=self.device)
         self.lib = _lib.load() if self.device.type == 'cuda' else None
         self._alloc_rollout()
         self.clear_actions()
@@ -72,13 +77,16 @@ class Agent(object):
         self.clear_actions()
 
     def reset_rnn_hiden(self):
-        self.hxs = torch.zeros(self.num_envs, self.num_agents, self.rnn_out, device=self.device)
-        self.cxs = torch.zeros(self.num_envs, self.num_agents, self.rnn_out, device=self.device)
+        self.hx_store.zero_()
+        self.cx_store.zero_()
+        self.hxs, self.cxs = self.hx_store, self.cx_store
 
     def update_rnn_hiden(self):
         """truncate BPTT at the rollout boundary (player_util.py:104-106)"""
-        self.hxs = self.hxs.detach()
-        self.cxs = self.cxs.detach()
+        if self.hxs is not self.hx_store:
+            self.hx_store.copy_(self.hxs.detach())
+            self.cx_store.copy_(self.cxs.detach())
+        self.hxs, self.cxs = self.hx_store, self.cx_store
 
     # ---- acting ----------------------------------------------------------------------------------
     def action_train(self, forced_actions=None, host=None):
@@ -107,7 +115,7 @@ class Agent(object):
         # envs that finished were reset by the env: their next step starts from zero LSTM state (train.py:73-74)
         keep = (1 - self.done.to(hxs.dtype)).view(-1, 1, 1)
         self.hxs, self.cxs = hxs * keep, cxs * keep
-        self.eps_len = (self.eps_len + 1) * (1 - self.done.to(torch.int32))
+        self.eps_len.add_(1).mul_(1 - self.done.to(torch.int32))
         self.n_steps += self.num_envs
         self.values.append(value)
         self.entropies.append(entropy)
@@ -128,7 +136,7 @@ class Agent(object):
         self.state = self.obs_buf[0]
         keep = (1 - done.to(hxs.dtype)).view(-1, 1, 1)
         self.hxs, self.cxs = hxs * keep, cxs * keep
-        self.eps_len = (self.eps_len + 1) * (1 - done.to(torch.int32))
+        self.eps_len.add_(1).mul_(1 - done.to(torch.int32))
         self.n_steps += self.num_envs
         return self
 
@@ -160,7 +168,11 @@ class Agent(object):
         values = torch.stack(self.values, 0)        # (T, E, 2)
         log_probs = torch.stack(self.log_probs, 0)  # (T, E, 2)
         entropies = torch.stack(self.entropies, 0)  # (T, E, 2)
-        w_ent = torch.tensor([float(self.args.entropy), float(self.w_entropy_target)], device=self.device)
+        key = (float(self.args.entropy), float(self.w_entropy_target))
+        if key != self._w_ent_key:  # w_entropy_target is assigned after construction (train.py:53)
+            self._w_ent_key = key
+            self.w_ent = torch.tensor(list(key), device=self.device)
+        w_ent = self.w_ent
         advantage = returns - values
         value_loss = (0.5 * advantage.pow(2)).sum(0)                       # (E, 2)   :133
         policy_loss = (-(log_probs * gae) - w_ent * entropies).sum(0)      # (E, 2)   :137-139
@@ -187,4 +199,7 @@ class Agent(object):
         self.clear_actions()
         self.obs_buf.data[0].copy_(self.state)
         self.state = self.obs_buf[0]
+        self.hx_store.copy_(self.hxs.detach())  # the next rollout starts from the stored state (fixed addresses)
+        self.cx_store.copy_(self.cxs.detach())
+        self.hxs, self.cxs = self.hx_store, self.cx_store
         return policy_loss.detach(), value_loss.detach(), entropies.detach().sum(0), pred_loss.detach()

@@ -59,8 +59,9 @@ class SharedAdam(object):
         self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
         z = lambda: torch.zeros_like(self.fp.flat)  # noqa: E731
         self.exp_avg, self.exp_avg_sq, self.max_exp_avg_sq = z(), z(), z()
-        self.step_count = 0
-        self.norm_scratch = torch.zeros(1, dtype=torch.float32, device=self.fp.flat.device)
+        self.step_count = 0  # host mirror of the device-resident update counter
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=self.fp.flat.device)
+        self.norm_scratch = torch.zeros(2, dtype=torch.float32, device=self.fp.flat.device)
 
     def share_memory(self):  # single process per GPU: nothing to share
         return self
@@ -75,17 +76,22 @@ class SharedAdam(object):
         _lib.check(self.lib.track2d_sharedadam_step(
             p(self.fp.flat), p(self.fp.grad), p(self.exp_avg), p(self.exp_avg_sq), p(self.max_exp_avg_sq), self.fp.numel,
             self.step_count, self.lr, self.betas[0], self.betas[1], self.eps, float(max_grad_norm or 0.0), float(grad_scale),
-            p(self.norm_scratch), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), self.lib)
+            p(self.norm_scratch), p(self.step_dev), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), self.lib)
+
+    def advance_for_replay(self):
+        """a CUDA-graph replay of step() advances the device counter by itself; keep the host mirror in sync"""
+        self.step_count += 1
 
     def grad_norm(self):
-        """total gradient norm seen by the last step (before clipping)"""
-        return float(self.norm_scratch.sqrt().item())
+        """total gradient norm seen by the last step (before clipping; only computed when clipping is on)"""
+        return float(self.norm_scratch[0].sqrt().item())
 
     def state_dict(self):
         return dict(step=self.step_count, exp_avg=self.exp_avg, exp_avg_sq=self.exp_avg_sq, max_exp_avg_sq=self.max_exp_avg_sq)
 
     def load_state_dict(self, sd):
         self.step_count = int(sd['step'])
+        self.step_dev.fill_(self.step_count)
         self.exp_avg.copy_(sd['exp_avg'])
         self.exp_avg_sq.copy_(sd['exp_avg_sq'])
         self.max_exp_avg_sq.copy_(sd['max_exp_avg_sq'])

@@ -109,6 +109,39 @@ class Trainer(object):
         self.n_iter += 1
         return out
 
+    # ---- CUDA-graph replay of the whole iteration ------------------------------------------------------------
+    def capture(self, training_mode=None, warmup=3):
+        """Capture one full iteration -- 20 x (policy forward, env.step, auto-reset), bootstrap, GAE, losses, backward,
+        [NCCL all-reduce], fused SharedAdam -- into ONE CUDA graph.  A rollout is ~4,300 kernel launches; below
+        ~16k envs per GPU the Python/driver launch path, not the GPU, bounds the step, and a graph replay removes it.
+        Everything inside is already stream-ordered with static shapes and no host synchronisation (the env kernels
+        are plain launches on the capturing stream), which is what makes the capture legal."""
+        mode = self.args.train_mode if training_mode is None else training_mode
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):  # warm up allocator, cuBLAS workspaces and autograd on the capture stream
+            for _ in range(warmup):
+                self.iteration(mode)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        self._graph = torch.cuda.CUDAGraph()
+        # (the optimizer's update count lives in device memory and is advanced by the captured kernels themselves;
+        # capture only records, so the counters below are untouched until the first replay)
+        step0, iter0, nsteps0 = self.optimizer.step_count, self.n_iter, self.player.n_steps
+        with torch.cuda.graph(self._graph, stream=side):
+            self._graph_out = self.iteration(mode)
+        self.optimizer.step_count, self.n_iter, self.player.n_steps = step0, iter0, nsteps0
+        self._graph_mode = mode
+        return self
+
+    def replay(self):
+        """one captured iteration; returns the same tensors as iteration() (overwritten by the next replay)"""
+        self.optimizer.advance_for_replay()
+        self._graph.replay()
+        self.n_iter += 1
+        self.player.n_steps += self.args.num_steps * self.args.num_envs
+        return self._graph_out
+
     def env_steps_per_iteration(self):
         return self.args.num_steps * self.args.num_envs
 

@@ -167,10 +167,13 @@ int track2d_get_counters(track2d_env *env, uint64_t *episodes_done, uint64_t *st
  * old-style bias correction) over one flat fp32 parameter vector.  All pointers are device pointers
  * of n floats; `step` is the 1-based update count (state['step'] after the increment);
  * `grad_scale` multiplies the gradient first (1/world_size after a sum-allreduce).
- * `norm_scratch_dev` is one float of scratch (the squared global norm). */
+ * `norm_scratch_dev` is TWO floats of scratch (squared global norm, step size).  If `step_dev` is not NULL it points to
+ * a device-resident int64 update counter that the call increments and uses instead of `step` (the bias correction is then
+ * computed on the device): that form can be captured in a CUDA graph and replayed. */
 int track2d_sharedadam_step(float *param_dev, const float *grad_dev, float *exp_avg_dev, float *exp_avg_sq_dev,
                             float *max_exp_avg_sq_dev, int64_t n, int64_t step, double lr, double beta1, double beta2,
-                            double eps, double max_grad_norm, double grad_scale, float *norm_scratch_dev, void *stream);
+                            double eps, double max_grad_norm, double grad_scale, float *norm_scratch_dev, int64_t *step_dev,
+                            void *stream);
 
 /* The backward recursion of Agent.optimize (player_util.py:127-140) for all envs: n-step returns R_t and
  * GAE advantages, cut at episode ends.  rewards [T][E][2], done [T][E], values [T+1][E][2] (row T = the

@@ -204,3 +204,33 @@ def test_evaluator_statistics_and_checkpoints(tmp_path):
     assert list(sd.keys()) == list(a3c_oracle.det_state_dict(tat=True).keys())
     gym_eval.load_weights(tr.model, load_tracker=os.path.join(tmp_path, "tracker-best.dat"), load_target=os.path.join(tmp_path, "target-best.dat"))
     tr.env.close()
+
+
+def test_cuda_graph_replay_of_the_whole_iteration():
+    """Trainer.capture(): one CUDA graph holds 20 x (policy, env.step, auto-reset) + update; replays keep learning,
+    advance the device-resident Adam counter, carry the LSTM / env state across replays and match eager statistically."""
+    from active_tracking_rl_b200.train import Trainer, default_args
+    tr = Trainer(default_args(num_envs=1024, seed=4), "cuda:0")
+    tr.capture(warmup=3)
+    assert tr.optimizer.step_count == 3 and int(tr.optimizer.step_dev.item()) == 3
+    w_prev = tr.optimizer.fp.flat.clone()
+    vls, eps0 = [], tr.env.counters()[0]
+    for k in range(40):
+        pl, vl, ent, prl = tr.replay()
+        if k % 10 == 9:
+            assert bool(torch.isfinite(vl).all())
+            w = tr.optimizer.fp.flat
+            assert float((w - w_prev).abs().max()) > 0  # every replay applies an update
+            w_prev = w.clone()
+        vls.append(float(vl.mean()))
+    assert int(tr.optimizer.step_dev.item()) == 43 == tr.optimizer.step_count
+    assert np.mean(vls[-5:]) < np.mean(vls[:5]), (vls[:5], vls[-5:])
+    assert tr.env.counters()[0] > eps0  # episodes keep finishing and resetting inside the graph
+    ctr = tr.env.get_agents()[1]
+    assert ctr[:, 1].max() > 20, "elapsed-step counters must carry across replays"
+    assert float(tr.player.hx_store.abs().max()) > 0
+    assert tr.env.status() == 0
+    # eager and replay agree statistically: the same trainer continues eagerly without a jump in the losses
+    pl, vl, ent, prl = tr.iteration()
+    assert abs(float(vl.mean()) - np.mean(vls[-5:])) < 0.5 * max(np.mean(vls[-5:]), 1.0)
+    tr.env.close()

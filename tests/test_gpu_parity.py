@@ -382,13 +382,13 @@ def test_sharedadam_kernel_matches_reference_formula(t2d):
     p = torch.randn(n, device="cuda", generator=g)
     m, v, vmax = torch.zeros_like(p), torch.zeros_like(p), torch.zeros_like(p)
     pr, mr, vr, xr = p.clone().double(), m.clone().double(), v.clone().double(), vmax.clone().double()
-    scratch = torch.zeros(1, device="cuda")
+    scratch = torch.zeros(2, device="cuda")
     lr, b1, b2, eps, maxn = 1e-3, 0.9, 0.999, 1e-3, 50.0
     for step in range(1, 6):
         grad = torch.randn(n, device="cuda", generator=g) * (0.2 if step % 2 else 0.01)
         _lib.check(lib.track2d_sharedadam_step(C.c_void_p(p.data_ptr()), C.c_void_p(grad.data_ptr()), C.c_void_p(m.data_ptr()),
                                                C.c_void_p(v.data_ptr()), C.c_void_p(vmax.data_ptr()), n, step, lr, b1, b2, eps, maxn, 1.0,
-                                               C.c_void_p(scratch.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+                                               C.c_void_p(scratch.data_ptr()), None, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
         # shared_optim.py:122-175 + clip_grad_norm_, in float64
         gd = grad.double()
         total = gd.norm()
