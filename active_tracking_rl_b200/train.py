@@ -128,8 +128,10 @@ class Trainer(object):
         # (the optimizer's update count lives in device memory and is advanced by the captured kernels themselves;
         # capture only records, so the counters below are untouched until the first replay)
         step0, iter0, nsteps0 = self.optimizer.step_count, self.n_iter, self.player.n_steps
+        l0 = self.env.lib.track2d_launch_count()
         with torch.cuda.graph(self._graph, stream=side):
             self._graph_out = self.iteration(mode)
+        self.launches_per_replay = int(self.env.lib.track2d_launch_count() - l0)  # libtrack2d kernels inside one replay
         self.optimizer.step_count, self.n_iter, self.player.n_steps = step0, iter0, nsteps0
         self._graph_mode = mode
         return self

@@ -254,8 +254,21 @@ def run_gpu_arm(a):
     # ---- the full path --------------------------------------------------------------------------------
     args = default_args(env=ENV_ID, num_envs=E, num_steps=T, seed=1)
     tr = Trainer(args, dev, rank, world)
+    # The whole iteration (4,300 launches) is replayed as ONE CUDA graph unless --no-graph; eager fallback if the
+    # capture is refused (e.g. a collective that cannot be captured on this NCCL build).
+    step_fn, mode = tr.iteration, "eager launches"
+    if not a.no_graph:
+        try:
+            tr.capture(warmup=2)
+            step_fn, mode = tr.replay, "one CUDA graph replay per step"
+        except Exception as ex:  # noqa: BLE001
+            if rank == 0:
+                sys.stderr.write("CUDA-graph capture failed (%s); running eagerly\n" % (str(ex).splitlines()[0],))
+            torch.cuda.synchronize()
+            tr = Trainer(args, dev, rank, world)
+            step_fn = tr.iteration
     for _ in range(a.warmup):
-        tr.iteration()
+        step_fn()
     sampler = ClockSampler(local_rank)
     barrier()
     if rank == 0:
@@ -264,10 +277,12 @@ def run_gpu_arm(a):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(a.steps):
-        tr.iteration()
+        step_fn()
     e1.record()
     barrier()
     launches = lib.track2d_launch_count() - l0
+    if step_fn == getattr(tr, "replay", None) and hasattr(tr, "launches_per_replay"):
+        launches = tr.launches_per_replay * a.steps  # kernels of ours inside the replayed graphs
     clocks = sampler.stop() if rank == 0 else None
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     ms_per_step = ms_total / a.steps
@@ -307,7 +322,7 @@ def run_gpu_arm(a):
         "config": {"workload": "%s, %d envs per GPU, tat-maze-lstm tracker+target + aux reward (full AD-VAT), rollout %d steps + 1 update per step"
                                % (ENV_ID, E, T), "envs_per_gpu": E, "rollout_steps": T, "parallelism": "dp%d" % world,
                    "rng": "philox", "l2": "rollout observation buffers (21 x %.0f MB) and the roofline ring exceed the 126 MB L2" % (obs_b / 1e6),
-                   "policy_math": "float32 (TF32 off)", "max_grad_norm": args.max_grad_norm},
+                   "policy_math": "float32 (TF32 off)", "max_grad_norm": args.max_grad_norm, "launch_mode": mode},
         "roofline": roofline, "env_only": env_only, "cpu_baseline": cpu_base, "e2e": e2e, "clocks": clocks,
         "gpu_launches": int(launches), "device_status": status, "replicas_identical": replicas_identical,
     }
@@ -324,6 +339,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying one CUDA graph per step")
     ap.add_argument("--traffic-bytes", type=float, default=60907008.0,
                     help="dram__bytes_read.sum + dram__bytes_write.sum per step-kernel launch from the committed ncu capture "
                          "(profiles/ncu_r1_kernels.txt: 27.46 MB read + 33.44 MB written INSIDE the kernel; the 126 MB write-back L2 "
