@@ -254,10 +254,11 @@ def run_gpu_arm(a):
     # ---- the full path --------------------------------------------------------------------------------
     args = default_args(env=ENV_ID, num_envs=E, num_steps=T, seed=1)
     tr = Trainer(args, dev, rank, world)
-    # The whole iteration (4,300 launches) is replayed as ONE CUDA graph unless --no-graph; eager fallback if the
-    # capture is refused (e.g. a collective that cannot be captured on this NCCL build).
+    # Single GPU: the whole iteration (4,300 launches) is replayed as ONE CUDA graph unless --no-graph.  Multi-GPU runs
+    # launch eagerly: capturing the NCCL all-reduce inside the graph dead-locked on this image (torch 2.11 / NCCL 2.28),
+    # and at 65,536 envs per GPU the step is GPU-bound anyway (graph replay is worth ~5 % there).
     step_fn, mode = tr.iteration, "eager launches"
-    if not a.no_graph:
+    if not a.no_graph and world == 1:
         try:
             tr.capture(warmup=2)
             step_fn, mode = tr.replay, "one CUDA graph replay per step"
