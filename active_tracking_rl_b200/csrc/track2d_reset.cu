@@ -74,6 +74,15 @@ __device__ void maze_walk(uint32_t *bm, Rng &rng, double r) {
     }
 }
 
+// Philox words generated ahead by the whole warp (see reset_env_philox), consumed by the sequential maze walk: keeps the
+// ten-round Philox out of lane 0's critical path.  interval(max) = floor(u32 * (max + 1) / 2^32) (bias <= 41 / 2^32).
+#define T2D_WALK_WORDS 1232 /* >= 47 seeds x (2 + 24 steps) */
+struct WordStream {
+    const uint32_t *w;
+    int i;
+    __device__ __forceinline__ uint32_t interval(uint32_t max) { return __umulhi(w[i++], max + 1u); }
+};
+
 // number of free cells, and the j-th free cell in row-major order (np.where(maze == 0) order).
 // Each lane owns 9 consecutive words of the grid.
 __device__ int bm_count_free(const uint32_t *bm, int lane) {
@@ -311,7 +320,8 @@ __device__ void nav_plan_from(const World &w, int e, Policy &P, int slot, int sr
 // ---- Philox reset ----------------------------------------------------------------------------------
 // `nav` is non-NULL only for the Nav / RPF instantiation (it then also provides bm).
 template <typename ObsT, int MAP>
-__device__ __noinline__ void reset_env_philox(const World &w, int e, uint32_t *bm, PhiloxNavScratch *nav, int slot, ObsT *obs, int lane, bool init_only) {
+__device__ __noinline__ void reset_env_philox(const World &w, int e, uint32_t *bm, uint32_t *walkw, PhiloxNavScratch *nav, int slot, ObsT *obs, int lane,
+                                              bool init_only) {
     const uint32_t episode = w.episode[e];
     Philox rng; // stream 0: the same on every lane (scalar decisions need no shuffles)
     rng.init(w.seed, (uint32_t)e, episode, 0u);
@@ -319,10 +329,22 @@ __device__ __noinline__ void reset_env_philox(const World &w, int e, uint32_t *b
 
     if (MAP == T2D_MAP_MAZE) {
         double r = w.level > 0 ? w.level * 0.02 : .03 * rng.dbl();
-        if (lane == 0) {
+        {   // every lane fills its share of the word stream (block b -> words 4b..4b+3), then lane 0 walks
+            const int density = (int)(r * 1600.0), complexity = (int)(r * 810.0);
+            const int need = density * (2 + complexity);
             Philox walk;
             walk.init(w.seed, (uint32_t)e, episode, 2u);
-            maze_walk(bm, walk, r);
+            for (int b = lane; 4 * b < need; b += 32) {
+                walk.blk = (uint32_t)b;
+                walk.block();
+#pragma unroll
+                for (int q = 0; q < 4; q++) walkw[4 * b + q] = walk.out[q];
+            }
+            __syncwarp();
+            if (lane == 0) {
+                WordStream ws{walkw, 0};
+                maze_walk(bm, ws, r);
+            }
         }
         __syncwarp();
     } else {
@@ -456,6 +478,7 @@ __device__ __noinline__ void reset_env_philox(const World &w, int e, uint32_t *b
 template <typename ObsT, int MAP>
 __global__ void __launch_bounds__(128) reset_philox_kernel(World w, const uint8_t *__restrict__ mask, int from_list, ObsT *obs, int init_only) {
     __shared__ uint32_t bms[4][T2D_MAP_WORDS];
+    __shared__ uint32_t walkw[4][MAP == T2D_MAP_MAZE ? T2D_WALK_WORDS : 1];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int gw = blockIdx.x * 4 + wib, nw = gridDim.x * 4;
     const int n = from_list ? (int)w.work_count[0] : w.E;
@@ -463,7 +486,7 @@ __global__ void __launch_bounds__(128) reset_philox_kernel(World w, const uint8_
         int e = i;
         if (from_list) e = (int)w.work_list[i];
         else if (mask && !mask[e]) continue;
-        reset_env_philox<ObsT, MAP>(w, e, bms[wib], nullptr, 0, obs, lane, init_only != 0);
+        reset_env_philox<ObsT, MAP>(w, e, bms[wib], walkw[wib], nullptr, 0, obs, lane, init_only != 0);
         __syncwarp();
     }
     if (from_list) finish_reset(w);
@@ -473,13 +496,14 @@ __global__ void __launch_bounds__(128) reset_philox_kernel(World w, const uint8_
 template <typename ObsT, int MAP>
 __global__ void __launch_bounds__(32) reset_philox_nav_kernel(World w, const uint8_t *__restrict__ mask, int from_list, ObsT *obs, int init_only) {
     __shared__ PhiloxNavScratch s;
+    __shared__ uint32_t walkw[MAP == T2D_MAP_MAZE ? T2D_WALK_WORDS : 1];
     const int lane = threadIdx.x;
     const int n = from_list ? (int)w.work_count[0] : w.E;
     for (int i = blockIdx.x; i < n; i += gridDim.x) {
         int e = i;
         if (from_list) e = (int)w.work_list[i];
         else if (mask && !mask[e]) continue;
-        reset_env_philox<ObsT, MAP>(w, e, s.bm, &s, blockIdx.x, obs, lane, init_only != 0);
+        reset_env_philox<ObsT, MAP>(w, e, s.bm, walkw, &s, blockIdx.x, obs, lane, init_only != 0);
         __syncwarp();
     }
     if (from_list) finish_reset(w);

@@ -179,6 +179,8 @@ def run_gpu_arm(a):
         cpu_base = {"value": v, "unit": "env-steps/s", "cores": W, "kind": "port",
                     "sample": "%.0f s of %d Hogwild A3C workers (oracle port of train.py + gym-track2d), %s, tat-maze-lstm" % (a.cpu_seconds, W, ENV_ID)}
 
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL prints its version banner there)
     import torch
     import torch.distributed as dist
     from active_tracking_rl_b200 import _lib
