@@ -5,8 +5,7 @@
 // _siftdown) over keys [f, node] with f = g + float64 euclidean distance and Node.__lt__ = path_cost <
 // (Astar_solver.py:30-32,53-63,127).  The planner below replays exactly those array operations, one
 // lane per plan (the search is inherently sequential), with g / parent-action maps and the first
-// T2D_HEAP_SMEM heap entries in shared memory and the rest of the heap spilled to an HBM workspace.  Keys are compared
-// exactly in integer arithmetic (f_cmp), so the search needs no float64 at all.
+// T2D_HEAP_SMEM heap entries in shared memory and the rest of the heap spilled to an HBM workspace.
 //
 // Frontier.replace (Astar_solver.py:65-73,146-147) can never fire on a unit-cost 4-connected grid with
 // the euclidean heuristic (adjacent cells have path costs of opposite parity, and a node that could
@@ -21,83 +20,61 @@
 struct AStarScratch {
     uint16_t gcost[T2D_MAX_CELLS]; // 0xFFFF = never seen; bit 15 = explored; low 15 bits = path cost
     uint8_t pact[T2D_MAX_CELLS];   // action that led into the cell
-    unsigned long long hk[T2D_HEAP_SMEM]; // heap entries: cell | g << 16 | d2 << 32  (f = g + sqrt(d2))
+    double hf[T2D_HEAP_SMEM];
+    uint32_t hc[T2D_HEAP_SMEM];    // cell | g << 16
 };
 
 struct HeapView {
-    unsigned long long *sk; // shared part
-    unsigned long long *gk; // HBM spill (indices >= T2D_HEAP_SMEM)
-    __device__ __forceinline__ unsigned long long get(int i) const { return i < T2D_HEAP_SMEM ? sk[i] : gk[i - T2D_HEAP_SMEM]; }
-    __device__ __forceinline__ void set(int i, unsigned long long v) {
-        if (i < T2D_HEAP_SMEM) sk[i] = v; else gk[i - T2D_HEAP_SMEM] = v;
+    double *sf; uint32_t *sc; // shared part
+    double *gf; uint32_t *gc; // HBM spill (indices >= T2D_HEAP_SMEM)
+    __device__ __forceinline__ double f(int i) const { return i < T2D_HEAP_SMEM ? sf[i] : gf[i - T2D_HEAP_SMEM]; }
+    __device__ __forceinline__ uint32_t c(int i) const { return i < T2D_HEAP_SMEM ? sc[i] : gc[i - T2D_HEAP_SMEM]; }
+    __device__ __forceinline__ void set(int i, double fv, uint32_t cv) {
+        if (i < T2D_HEAP_SMEM) { sf[i] = fv; sc[i] = cv; } else { gf[i - T2D_HEAP_SMEM] = fv; gc[i - T2D_HEAP_SMEM] = cv; }
     }
 };
 
-// Exact comparison of f = g + sqrt(d2) without floating point.  The reference compares float64 values
-// g + np.linalg.norm(...) (Astar_solver.py:127,151-153).  For integers g <= 2^15, d2 <= 2 * 81^2 two such values are
-// either exactly equal (same g and d2, or perfect squares with equal sums -- float64 represents those exactly) or at
-// least ~4.5e-8 apart (|N - 2k sqrt(b)| >= 1 / (N + 2k sqrt(b)) for a non-square b), nine orders of magnitude more than
-// float64 rounding can move them: the integer test below therefore orders and ties exactly like the reference's
-// floats, and the heap needs neither a square root nor 8-byte float keys.
-// Returns -1 / 0 / +1 for  ga + sqrt(da)  <, ==, >  gb + sqrt(db).
-__device__ __forceinline__ int f_cmp(int ga, int da, int gb, int db) {
-    int k = gb - ga; // sign(sqrt(da) - sqrt(db) - k)
-    if (k == 0) return da < db ? -1 : (da > db ? 1 : 0);
-    bool flip = k < 0;
-    if (flip) { k = -k; int t = da; da = db; db = t; } // now: sign(sqrt(da) - sqrt(db) - k), k > 0, result negated if flipped
-    int r;
-    if (da <= db) {
-        r = -1;
-    } else {
-        long long L = (long long)da - db - (long long)k * k; // sqrt(da) - sqrt(db) < k  <=>  L < 2 k sqrt(db)
-        if (L < 0) {
-            r = -1;
-        } else {
-            long long lhs = L * L, rhs = 4ll * k * k * db;
-            r = lhs < rhs ? -1 : (lhs > rhs ? 1 : 0);
-        }
-    }
-    return flip ? -r : r;
-}
-
-// [f, node] < [f2, node2]: floats first; on equal f Node.__lt__ (path_cost <), Astar_solver.py:30-32,55
-__device__ __forceinline__ bool heap_lt(unsigned long long a, unsigned long long b) {
-    int ga = (int)((a >> 16) & 0xFFFFu), gb = (int)((b >> 16) & 0xFFFFu);
-    int c = f_cmp(ga, (int)(a >> 32), gb, (int)(b >> 32));
-    return c != 0 ? c < 0 : ga < gb;
+// [f, node] < [f2, node2]
+__device__ __forceinline__ bool heap_lt(double fa, uint32_t ca, double fb, uint32_t cb) {
+    return fa != fb ? fa < fb : (ca >> 16) < (cb >> 16);
 }
 
 __device__ __forceinline__ void hq_siftdown(HeapView &h, int startpos, int pos) { // heapq._siftdown
-    const unsigned long long nv = h.get(pos);
+    double nf = h.f(pos);
+    uint32_t nc = h.c(pos);
     while (pos > startpos) {
         int parent = (pos - 1) >> 1;
-        unsigned long long pv = h.get(parent);
-        if (heap_lt(nv, pv)) {
-            h.set(pos, pv);
+        double pf = h.f(parent);
+        uint32_t pc = h.c(parent);
+        if (heap_lt(nf, nc, pf, pc)) {
+            h.set(pos, pf, pc);
             pos = parent;
             continue;
         }
         break;
     }
-    h.set(pos, nv);
+    h.set(pos, nf, nc);
 }
 
 __device__ __forceinline__ void hq_siftup(HeapView &h, int pos, int endpos) { // heapq._siftup
     int startpos = pos;
-    const unsigned long long nv = h.get(pos);
+    double nf = h.f(pos);
+    uint32_t nc = h.c(pos);
     int child = 2 * pos + 1;
     while (child < endpos) {
         int right = child + 1;
-        unsigned long long cv = h.get(child);
+        double cf = h.f(child);
+        uint32_t cc = h.c(child);
         if (right < endpos) {
-            unsigned long long rv = h.get(right);
-            if (!heap_lt(cv, rv)) { child = right; cv = rv; }
+            double rf = h.f(right);
+            uint32_t rc = h.c(right);
+            if (!heap_lt(cf, cc, rf, rc)) { child = right; cf = rf; cc = rc; }
         }
-        h.set(pos, cv);
+        h.set(pos, cf, cc);
         pos = child;
         child = 2 * pos + 1;
     }
-    h.set(pos, nv);
+    h.set(pos, nf, nc);
     hq_siftdown(h, startpos, pos);
 }
 
@@ -120,29 +97,31 @@ __device__ int astar_plan(const World &w, int e, const uint32_t *bm, AStarScratc
     int len = -1;
     if (lane == 0) {
         HeapView h;
-        h.sk = a.hk;
-        h.gk = reinterpret_cast<unsigned long long *>(w.astar_ws + (size_t)slot * T2D_MAX_CELLS * 12);
+        h.sf = a.hf; h.sc = a.hc;
+        h.gf = reinterpret_cast<double *>(w.astar_ws + (size_t)slot * T2D_MAX_CELLS * 12);
+        h.gc = reinterpret_cast<uint32_t *>(w.astar_ws + (size_t)slot * T2D_MAX_CELLS * 12 + (size_t)T2D_MAX_CELLS * 8);
         const int goal = gr * W + gc;
         int hn = 0;
         {
             int start = sr * W + sc;
-            int dr = sr - gr, dc = sc - gc;
+            double dr = (double)(sr - gr), dc = (double)(sc - gc);
             a.gcost[start] = 0;
-            h.set(0, (unsigned long long)start | ((unsigned long long)(dr * dr + dc * dc) << 32));
+            h.set(0, 0.0 + __dsqrt_rn(__dadd_rn(__dmul_rn(dr, dr), __dmul_rn(dc, dc))), (uint32_t)start);
             hn = 1;
         }
         int sol = -1;
         while (hn > 0) {
             // Frontier.pop == heapq.heappop
             hn--;
-            const unsigned long long last = h.get(hn);
-            unsigned long long top = last;
+            double lf = h.f(hn);
+            uint32_t lc = h.c(hn);
+            uint32_t top = lc;
             if (hn > 0) {
-                top = h.get(0);
-                h.set(0, last);
+                top = h.c(0);
+                h.set(0, lf, lc);
                 hq_siftup(h, 0, hn);
             }
-            int cell = (int)(top & 0xFFFFu), g = (int)((top >> 16) & 0xFFFFu);
+            int cell = top & 0xFFFFu, g = top >> 16;
             if (cell == goal) { sol = cell; break; }
             a.gcost[cell] |= 0x8000u; // explored.add
             int r = cell / W, c = cell - r * W;
@@ -155,9 +134,10 @@ __device__ int astar_plan(const World &w, int e, const uint32_t *bm, AStarScratc
                 if (gv == 0xFFFFu) {
                     a.gcost[child] = (uint16_t)(g + 1);
                     a.pact[child] = (uint8_t)act;
-                    int dr = nr - gr, dc = nc - gc;
-                    h.set(hn, (unsigned long long)child | ((unsigned long long)(g + 1) << 16) | ((unsigned long long)(dr * dr + dc * dc) << 32));
-                    hn++; // Frontier.add == heappush
+                    double dr = (double)(nr - gr), dc = (double)(nc - gc);
+                    double f = __dadd_rn((double)(g + 1), __dsqrt_rn(__dadd_rn(__dmul_rn(dr, dr), __dmul_rn(dc, dc))));
+                    h.set(hn, f, (uint32_t)child | ((uint32_t)(g + 1) << 16)); // Frontier.add == heappush
+                    hn++;
                     hq_siftdown(h, 0, hn - 1);
                 } else if (!(gv & 0x8000u) && (int)(gv & 0x7FFFu) < g + 1) {
                     atomicOr(w.status, (uint32_t)T2D_STATUS_ASTAR_REPLACE);

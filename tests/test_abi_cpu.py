@@ -74,30 +74,3 @@ def test_product_never_imports_the_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("test oracle", ""), "%s mentions the oracle" % f
 
-
-def test_astar_integer_key_comparison_equals_float64():
-    """csrc/track2d_nav.cuh compares f = g + sqrt(d2) in exact integer arithmetic (f_cmp).  Restated here and checked
-    against the reference's float64 comparison (g + np.linalg.norm) on every (d2a, d2b) reachable on the grid for the
-    path-cost differences the heap can see, incl. the exact ties that route to Node.__lt__."""
-    import numpy as np
-    d2 = np.unique((np.arange(0, 82)[:, None] ** 2 + np.arange(0, 82)[None, :] ** 2).ravel()).astype(np.int64)
-    rs = np.random.RandomState(1)
-    ties = 0
-    for k in range(-9, 10):
-        a = d2[rs.randint(0, len(d2), 60000)]
-        b = d2[rs.randint(0, len(d2), 60000)]
-        # add structured near-ties: neighbouring cells along a line through the goal
-        t = np.arange(1, 100, dtype=np.int64)
-        a = np.concatenate([a, t * t, (t + abs(k)) ** 2, 2 * t * t])
-        b = np.concatenate([b, (t + k) ** 2 * (t + k > 0), t * t, 2 * (t + 1) ** 2])
-        ref = np.sign((0.0 + np.sqrt(a.astype(np.float64))) - (float(k) + np.sqrt(b.astype(np.float64)))).astype(np.int64)
-        kk = abs(k)
-        aa, bb = (a, b) if k >= 0 else (b, a)
-        L = aa - bb - kk * kk
-        r = np.where(aa <= bb, -1, np.where(L < 0, -1, np.sign(L * L - 4 * kk * kk * bb)))
-        if k == 0:
-            r = np.sign(a - b)
-        got = r if k >= 0 else -r
-        assert (got == ref).all(), (k, int((got != ref).sum()))
-        ties += int((ref == 0).sum())
-    assert ties > 50
