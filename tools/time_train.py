@@ -7,7 +7,7 @@ from active_tracking_rl_b200.train import Trainer, default_args
 E = int(sys.argv[1]); iters = int(sys.argv[2])
 if len(sys.argv) > 3: M.CONV_IMPL = sys.argv[3]
 if len(sys.argv) > 4: torch.backends.cudnn.benchmark = bool(int(sys.argv[4]))
-tr = Trainer(default_args(num_envs=E), "cuda:0")
+tr = Trainer(default_args(num_envs=E, tf32=os.environ.get("TF32") == "1"), "cuda:0")
 use_graph = os.environ.get("GRAPH") == "1"
 if use_graph:
     tr.capture()
@@ -23,5 +23,5 @@ for _ in range(iters):
     out = step()
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / iters
-print("graph=%s " % use_graph + "E=%d conv=%s bench=%s  %.1f ms/iter  %.3e env-steps/s  mem=%.1f GB  vloss=%.4f" % (E, M.CONV_IMPL, torch.backends.cudnn.benchmark, ms, E * 20 / ms * 1e3,
+print("tf32=%s graph=%s " % (os.environ.get("TF32") == "1", use_graph) + "E=%d conv=%s bench=%s  %.1f ms/iter  %.3e env-steps/s  mem=%.1f GB  vloss=%.4f" % (E, M.CONV_IMPL, torch.backends.cudnn.benchmark, ms, E * 20 / ms * 1e3,
       torch.cuda.max_memory_allocated() / 1e9, float(out[1].mean())))
