@@ -20,6 +20,10 @@
 // HBM traffic per env-step (algorithmic): 1,755 B, of which 1,352 B is the fp32 obs write.
 #include "track2d_common.cuh"
 
+#ifndef T2D_STEP_FORCE_N
+#define T2D_STEP_FORCE_N 0 /* 16 or 32 pins the envs-per-CTA choice (tuning builds) */
+#endif
+
 namespace {
 
 template <typename ObsT>
@@ -196,8 +200,11 @@ __global__ void __launch_bounds__(THREADS) step_kernel(World w, const int32_t *_
     // the end of the batch are clamped onto the last valid env and masked afterwards), so a group costs one
     // memory latency, not four.
     constexpr int GROUPS = (26 * N) / 4;
-#pragma unroll 1
-    for (int g = tid; g < GROUPS; g += THREADS) {
+    constexpr int GITERS = (GROUPS + THREADS - 1) / THREADS;
+#pragma unroll
+    for (int git = 0; git < GITERS; git++) {
+        const int g = tid + git * THREADS;
+        if (g >= GROUPS) break;
         uint32_t lo_w[4], hi_w[4];
         int sh[4];
         bool ok[4];
@@ -281,10 +288,26 @@ __global__ void full_obs_kernel(World w, ObsT *__restrict__ obs, const uint8_t *
 
 template <int TARGET, int RNG, typename ObsT>
 cudaError_t launch_step_t(const World &w, const int32_t *actions, ObsT *obs, float *reward, uint8_t *done, cudaStream_t s) {
-    // 16 envs per CTA of 128 threads: 104 four-row groups -> at most one group per thread (a single load
-    // latency in phase B), 5.4 KB of staging, 16 CTAs (2048 threads) resident per SM.
-    constexpr int N = 16, T = 128;
-    step_kernel<TARGET, RNG, ObsT, N, T><<<(w.E + N - 1) / N, T, 0, s>>>(w, actions, obs, reward, done);
+    // 16 envs per CTA of 128 threads: 104 four-row groups -> at most one group per thread (a single load latency in
+    // phase B), 5.4 KB of staging, 16 CTAs (2048 threads) resident per SM = 37,888 envs per wave on 148 SMs.
+    // A CTA lives ~10 us (three dependent memory latencies), so batches between one and two waves (e.g. 65,536 envs =
+    // 1.73 waves) pay for two: those run 32 envs per CTA instead (two groups per thread, still 16 CTAs/SM resident,
+    // 75,776 envs per wave) and finish in ONE wave.  Large batches keep 16/CTA (96 % of the HBM roofline at 1 M envs).
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const long wave16 = (long)sms * 16 * 16, wave32 = (long)sms * 16 * 32;
+    const int force = T2D_STEP_FORCE_N;
+    if (force == 32 || (force == 0 && w.E > wave16 && w.E <= wave32)) {
+        constexpr int N = 32, T = 128;
+        step_kernel<TARGET, RNG, ObsT, N, T><<<(w.E + N - 1) / N, T, 0, s>>>(w, actions, obs, reward, done);
+    } else {
+        constexpr int N = 16, T = 128;
+        step_kernel<TARGET, RNG, ObsT, N, T><<<(w.E + N - 1) / N, T, 0, s>>>(w, actions, obs, reward, done);
+    }
     return cudaGetLastError();
 }
 
