@@ -350,9 +350,8 @@ __device__ __noinline__ void reset_env_philox(const World &w, int e, uint32_t *b
     } else {
         double r = MAP == T2D_MAP_EMPTY ? 0.0 : (w.level > 0 ? w.level * 0.05 : 0.15 * rng.dbl());
         int k = (int)(r * 6400.0); // generators.py:166
-        // Draw uniform interior cells until k distinct ones are set.  Processing a round of 32 draws in lane
-        // order (duplicates inside the round resolved to the lowest lane, surplus beyond k dropped from the
-        // high lanes) is the same process as drawing one at a time, i.e. a uniform k-subset.
+        // Draw uniform interior cells until exactly k distinct ones are set (a uniform k-subset, the law of
+        // np.random.choice(6400, k, replace=False)).
         Philox mine;
         mine.init(w.seed, (uint32_t)e, episode, 0x100u + (uint32_t)lane);
         int count = 0;
@@ -375,30 +374,36 @@ __device__ __noinline__ void reset_env_philox(const World &w, int e, uint32_t *b
             count += __reduce_add_sync(0xFFFFFFFFu, added);
         }
         __syncwarp();
+        // tail: fewer than 128 cells missing.  Four sub-rounds per Philox block; in each, every lane offers one cell, the
+        // old value of the atomicOr tells whether it was new, and if more were new than are still needed the surplus
+        // (highest lanes) is taken back.  The procedure never looks at WHICH cell a lane holds, so all k-subsets stay
+        // equally likely -- same law as the reference's sampling without replacement.
         while (count < k) {
             mine.block();
-            int cell = -1;
 #pragma unroll
-            for (int q = 0; q < 4; q++) { // first 13-bit candidate below 6400 (p(accept) = 0.78 each)
-                int cand = (int)(mine.out[q] & 8191u);
-                if (cell < 0 && cand < 6400) cell = cand;
+            for (int q = 0; q < 4; q++) {
+                if (count < k) { // warp-uniform
+                    const int cand = (int)(mine.out[q] & 8191u);
+                    bool fresh = false;
+                    uint32_t bit = 0;
+                    uint32_t *word = bm;
+                    if (cand < 6400) {
+                        const int rr = cand / 80 + 1, cq = cand - (rr - 1) * 80 + 1;
+                        bit = map_bit_of(cq);
+                        word = &bm[map_word_index(rr, cq)];
+                        fresh = !(atomicOr(word, bit) & bit);
+                    }
+                    const uint32_t fmask = __ballot_sync(0xFFFFFFFFu, fresh);
+                    const int need = k - count;
+                    int nf = __popc(fmask);
+                    if (nf > need) {
+                        if (fresh && __popc(fmask & ((1u << lane) - 1u)) >= need) atomicAnd(word, ~bit);
+                        nf = need;
+                    }
+                    count += nf;
+                }
             }
             mine.have = 0;
-            bool valid = cell >= 0;
-            uint32_t vmask = __ballot_sync(0xFFFFFFFFu, valid);
-            bool fresh = false;
-            int r_ = 0, c_ = 0;
-            if (valid) {
-                uint32_t peers = __match_any_sync(vmask, cell);
-                r_ = cell / 80 + 1;
-                c_ = cell - (r_ - 1) * 80 + 1;
-                fresh = (lane == __ffs(peers) - 1) && !bm_wall(bm, r_, c_);
-            }
-            uint32_t fmask = __ballot_sync(0xFFFFFFFFu, fresh);
-            int need = k - count;
-            int rank = __popc(fmask & ((1u << lane) - 1u));
-            if (fresh && rank < need) bm_set(bm, r_, c_);
-            count += min(need, __popc(fmask));
             __syncwarp();
         }
     }
