@@ -462,3 +462,51 @@ def test_philox_navigator_plans_are_valid_shortest_paths(t2d, env_id):
     assert replans > 0, "no plan ran out: the replan kernel was not exercised"
     assert env.status() == 0
     env.close()
+
+
+@pytest.mark.parametrize("env_id,E", [("Track2D-BlockFullPZR-v0", 37), ("Track2D-MazeFullRam-v0", 18), ("Track2D-EmptyFullFar-v1", 9)])
+def test_full_observation_batched_matches_oracle(t2d, env_id, E):
+    """obs_type 'Full' (track_1v1.py:288-290): both agents see the whole map, tracker = 2, then target = 4."""
+    S = 77
+    orc = _oracle_batch(env_id, E, S)
+    env = t2d.Track2DVecEnv(env_id, num_envs=E, seed=S, rng="numpy", auto_reset=True, keep_f64=True)
+    obs = env.reset().cpu().numpy()
+    H, W = env.H, env.W
+    assert obs.shape == (E, 2, 1, H, W) and env.observation_space[0].shape == (1, H, W)
+    for e, o in enumerate(orc):
+        assert (obs[e] == o.reset()).all(), e
+    rs = np.random.RandomState(5)
+    for t in range(40):
+        acts = rs.randint(0, 4, size=(E, 2)).astype(np.int32)
+        acts[:, 0] = 0 if t % 2 else acts[:, 0]
+        obs, rew, done = env.step(torch.from_numpy(acts).cuda())
+        obs, done = obs.cpu().numpy(), done.cpu().numpy()
+        r64 = env.get_rewards_f64()
+        for e, o in enumerate(orc):
+            oo, orew, odone, _ = o.step(acts[e])
+            assert r64[e].tobytes() == orew.tobytes() and bool(done[e]) == odone
+            if odone:
+                oo = o.reset()
+            assert (obs[e] == oo).all(), (t, e)
+    env.close()
+
+
+def test_gym_shim_surface_matches_reference_types(t2d):
+    """the drop-in surface of SURVEY 8(b): spaces are LISTS of two, reset/step return the reference's types and dtypes"""
+    env = t2d.make("Track2D-BlockPartialPZR-v0", seed=3)
+    assert isinstance(env.observation_space, list) and len(env.observation_space) == 2 and isinstance(env.action_space, list)
+    assert env.observation_space[0].shape == (1, 13, 13) and env.action_space[1].n == 4
+    assert env.seed(5) == [5]
+    obs = env.reset()
+    assert isinstance(obs, np.ndarray) and obs.shape == (2, 1, 13, 13) and obs.dtype == np.float64  # Block maps are float (generators.py:161)
+    out = env.step([np.array([1]), np.int64(2)])  # 1-element arrays and numpy ints are coerced with int() (track_1v1.py:87)
+    assert len(out) == 4
+    obs, rew, done, info = out
+    assert rew.dtype == np.float64 and rew.shape == (2,) and isinstance(done, bool) and "distance" in info and "traces" in info
+    assert env.unwrapped is env and len(env.state) == 2 and env.maze.shape == (82, 82)
+    with pytest.raises(NotImplementedError):
+        env.render()
+    env.close()
+    menv = t2d.make("Track2D-MazePartialAdv-v0", seed=3)
+    assert menv.reset().dtype == np.int64 and menv.maze.shape == (81, 81)  # Maze maps are int (generators.py:145)
+    menv.close()
