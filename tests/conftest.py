@@ -8,6 +8,10 @@ for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "oracle", "refh
     if p not in sys.path:
         sys.path.insert(0, p)
 
+if os.environ.get("TRACK2D_FP32_EMULATION") == "1":  # must precede the first `import torch`
+    from active_tracking_rl_b200 import blas
+    blas.enable_fp32_emulation(os.environ.get("CUBLAS_EMULATION_STRATEGY", "performant"))
+
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 

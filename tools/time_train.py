@@ -1,5 +1,9 @@
 """Time rollout+update iterations: python tools/time_train.py E iters [conv_impl] [cudnn_benchmark]"""
 import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+if os.environ.get("EMU") == "1":
+    from active_tracking_rl_b200 import blas
+    print("fp32 emulation:", blas.enable_fp32_emulation(os.environ.get("EMU_STRATEGY", "performant")), blas.status())
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from active_tracking_rl_b200 import model as M
