@@ -1,5 +1,9 @@
 """Profile one rollout+update iteration: python tools/prof_train.py E [iters]  -> kernel table on stdout"""
 import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+if os.environ.get("EMU") == "1":
+    from active_tracking_rl_b200 import blas
+    blas.enable_fp32_emulation(os.environ.get("EMU_STRATEGY", "performant"))
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from active_tracking_rl_b200.train import Trainer, default_args
