@@ -14,6 +14,7 @@ import time
 
 import torch
 
+from . import blas
 from .environment import create_env
 from .model import build_model
 from .player_util import Agent
@@ -52,6 +53,7 @@ def make_parser():
     p.add_argument('--iters', type=int, default=100, help='rollout+update iterations to run')
     p.add_argument('--max-grad-norm', type=float, default=0.0,
                    help='0 = the reference\'s effective behaviour (its clip_grad_norm_(params, 50) is inert); 50 = its intent')
+    p.add_argument('--fp32-emulation', action='store_true', help='fp32 GEMMs through cuBLAS 12.9 BF16x9 emulation (see blas.py)')
     p.add_argument('--tf32', action='store_true', help='allow TF32 tensor-core math in the policy (off: float32 like the reference)')
     return p
 
@@ -153,6 +155,10 @@ class Trainer(object):
 
 def main():
     args = make_parser().parse_args()
+    if args.fp32_emulation and not blas.status()["enabled"]:
+        print("note: --fp32-emulation needs `blas.enable_fp32_emulation()` before torch is imported; run through "
+              "`python -c 'from active_tracking_rl_b200 import blas; blas.enable_fp32_emulation(); "
+              "from active_tracking_rl_b200 import train; train.main()' ...`")
     args.single = False
     rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))

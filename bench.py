@@ -179,6 +179,11 @@ def run_gpu_arm(a):
         cpu_base = {"value": v, "unit": "env-steps/s", "cores": W, "kind": "port",
                     "sample": "%.0f s of %d Hogwild A3C workers (oracle port of train.py + gym-track2d), %s, tat-maze-lstm" % (a.cpu_seconds, W, ENV_ID)}
 
+    emu = None
+    if a.fp32_emulation:  # must happen before torch is imported (see active_tracking_rl_b200/blas.py)
+        from active_tracking_rl_b200 import blas
+        blas.enable_fp32_emulation()
+        emu = blas.status()
     if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
         os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL prints its version banner there)
     import torch
@@ -325,7 +330,8 @@ def run_gpu_arm(a):
         "config": {"workload": "%s, %d envs per GPU, tat-maze-lstm tracker+target + aux reward (full AD-VAT), rollout %d steps + 1 update per step"
                                % (ENV_ID, E, T), "envs_per_gpu": E, "rollout_steps": T, "parallelism": "dp%d" % world,
                    "rng": "philox", "l2": "rollout observation buffers (21 x %.0f MB) and the roofline ring exceed the 126 MB L2" % (obs_b / 1e6),
-                   "policy_math": "float32 (TF32 off)", "max_grad_norm": args.max_grad_norm, "launch_mode": mode},
+                   "policy_math": "float32 (TF32 off)" + ("; GEMMs via " + emu["reason"] if emu and emu["enabled"] else "; cuBLAS SIMT SGEMM"),
+                   "max_grad_norm": args.max_grad_norm, "launch_mode": mode},
         "roofline": roofline, "env_only": env_only, "cpu_baseline": cpu_base, "e2e": e2e, "clocks": clocks,
         "gpu_launches": int(launches), "device_status": status, "replicas_identical": replicas_identical,
     }
@@ -342,6 +348,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fp32-emulation", action="store_true",
+                    help="route the policy's fp32 GEMMs through cuBLAS 12.9 BF16x9 emulation (fp32-accurate, tensor cores); off = SIMT SGEMM")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying one CUDA graph per step")
     ap.add_argument("--traffic-bytes", type=float, default=60907008.0,
                     help="dram__bytes_read.sum + dram__bytes_write.sum per step-kernel launch from the committed ncu capture "
