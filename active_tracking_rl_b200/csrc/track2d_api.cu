@@ -39,6 +39,7 @@ struct track2d_env {
     // device staging for the host-buffer API
     int32_t *d_actions;
     float *d_obs;
+    uint8_t *d_obs8;
     float *d_reward;
     uint8_t *d_done;
     uint8_t *d_mask;
@@ -197,7 +198,7 @@ int track2d_create(const track2d_config *cfg, track2d_env **out) {
     env->cfg = *cfg;
     env->was_reset = false;
     env->steps_done = 0;
-    env->d_actions = nullptr; env->d_obs = nullptr; env->d_reward = nullptr; env->d_done = nullptr; env->d_mask = nullptr;
+    env->d_actions = nullptr; env->d_obs = nullptr; env->d_obs8 = nullptr; env->d_reward = nullptr; env->d_done = nullptr; env->d_mask = nullptr;
     World &w = env->w;
     memset(&w, 0, sizeof(w));
     const int E = cfg->num_envs;
@@ -296,48 +297,79 @@ int track2d_step_u8(track2d_env *env, const int32_t *actions_dev, uint8_t *obs_d
 }
 
 // ---- host-buffer API -------------------------------------------------------------------------------
-static int ensure_staging(track2d_env *env) {
-    if (env->d_obs) return T2D_OK;
+} // extern "C" (the templated helpers below need C++ linkage)
+
+static int ensure_staging(track2d_env *env, bool u8 = false) {
     const size_t E = (size_t)env->w.E, cells = (size_t)cells_of(env);
-    int rc = dev_alloc(env, &env->d_actions, 2 * E);
-    if (rc == T2D_OK) rc = dev_alloc(env, &env->d_obs, E * 2 * cells);
-    if (rc == T2D_OK) rc = dev_alloc(env, &env->d_reward, 2 * E);
-    if (rc == T2D_OK) rc = dev_alloc(env, &env->d_done, E);
-    if (rc == T2D_OK) rc = dev_alloc(env, &env->d_mask, E);
+    int rc = T2D_OK;
+    if (!env->d_actions) {
+        rc = dev_alloc(env, &env->d_actions, 2 * E);
+        if (rc == T2D_OK) rc = dev_alloc(env, &env->d_reward, 2 * E);
+        if (rc == T2D_OK) rc = dev_alloc(env, &env->d_done, E);
+        if (rc == T2D_OK) rc = dev_alloc(env, &env->d_mask, E);
+    }
+    if (rc == T2D_OK && !u8 && !env->d_obs) rc = dev_alloc(env, &env->d_obs, E * 2 * cells);
+    if (rc == T2D_OK && u8 && !env->d_obs8) rc = dev_alloc(env, &env->d_obs8, E * 2 * cells + 16);
     return rc;
 }
 
-int track2d_reset_host(track2d_env *env, const uint8_t *mask_host, float *obs_host) {
-    T2D_REQUIRE(env, "null handle");
-    DeviceGuard guard(env->cfg.device);
-    int rc = ensure_staging(env);
+template <typename ObsT>
+static int step_host_t(track2d_env *env, const int32_t *actions_host, ObsT *obs_host, float *reward_host, uint8_t *done_host) {
+    constexpr bool u8 = sizeof(ObsT) == 1;
+    int rc = ensure_staging(env, u8);
     if (rc != T2D_OK) return rc;
     cudaStream_t s = env->own_stream;
     const size_t E = (size_t)env->w.E, cells = (size_t)cells_of(env);
-    if (mask_host) T2D_CUDA(cudaMemcpyAsync(env->d_mask, mask_host, E, cudaMemcpyHostToDevice, s));
-    rc = do_reset<float>(env, mask_host ? env->d_mask : nullptr, env->d_obs, 0, s);
-    if (rc != T2D_OK) return rc;
-    if (obs_host) T2D_CUDA(cudaMemcpyAsync(obs_host, env->d_obs, E * 2 * cells * sizeof(float), cudaMemcpyDeviceToHost, s));
-    T2D_CUDA(cudaStreamSynchronize(s));
-    return T2D_OK;
-}
-
-int track2d_step_host(track2d_env *env, const int32_t *actions_host, float *obs_host, float *reward_host, uint8_t *done_host) {
-    T2D_REQUIRE(env, "null handle");
-    T2D_REQUIRE(actions_host, "step_host: actions required");
-    DeviceGuard guard(env->cfg.device);
-    int rc = ensure_staging(env);
-    if (rc != T2D_OK) return rc;
-    cudaStream_t s = env->own_stream;
-    const size_t E = (size_t)env->w.E, cells = (size_t)cells_of(env);
+    ObsT *d_obs = u8 ? (ObsT *)env->d_obs8 : (ObsT *)env->d_obs;
     T2D_CUDA(cudaMemcpyAsync(env->d_actions, actions_host, 2 * E * sizeof(int32_t), cudaMemcpyHostToDevice, s));
-    rc = do_step<float>(env, env->d_actions, env->d_obs, env->d_reward, env->d_done, s);
+    rc = do_step<ObsT>(env, env->d_actions, d_obs, env->d_reward, env->d_done, s);
     if (rc != T2D_OK) return rc;
-    if (obs_host) T2D_CUDA(cudaMemcpyAsync(obs_host, env->d_obs, E * 2 * cells * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (obs_host) T2D_CUDA(cudaMemcpyAsync(obs_host, d_obs, E * 2 * cells * sizeof(ObsT), cudaMemcpyDeviceToHost, s));
     if (reward_host) T2D_CUDA(cudaMemcpyAsync(reward_host, env->d_reward, 2 * E * sizeof(float), cudaMemcpyDeviceToHost, s));
     if (done_host) T2D_CUDA(cudaMemcpyAsync(done_host, env->d_done, E, cudaMemcpyDeviceToHost, s));
     T2D_CUDA(cudaStreamSynchronize(s));
     return T2D_OK;
+}
+
+template <typename ObsT>
+static int reset_host_t(track2d_env *env, const uint8_t *mask_host, ObsT *obs_host) {
+    constexpr bool u8 = sizeof(ObsT) == 1;
+    int rc = ensure_staging(env, u8);
+    if (rc != T2D_OK) return rc;
+    cudaStream_t s = env->own_stream;
+    const size_t E = (size_t)env->w.E, cells = (size_t)cells_of(env);
+    ObsT *d_obs = u8 ? (ObsT *)env->d_obs8 : (ObsT *)env->d_obs;
+    if (mask_host) T2D_CUDA(cudaMemcpyAsync(env->d_mask, mask_host, E, cudaMemcpyHostToDevice, s));
+    rc = do_reset<ObsT>(env, mask_host ? env->d_mask : nullptr, d_obs, 0, s);
+    if (rc != T2D_OK) return rc;
+    if (obs_host) T2D_CUDA(cudaMemcpyAsync(obs_host, d_obs, E * 2 * cells * sizeof(ObsT), cudaMemcpyDeviceToHost, s));
+    T2D_CUDA(cudaStreamSynchronize(s));
+    return T2D_OK;
+}
+
+extern "C" {
+
+int track2d_reset_host(track2d_env *env, const uint8_t *mask_host, float *obs_host) {
+    T2D_REQUIRE(env, "null handle");
+    DeviceGuard guard(env->cfg.device);
+    return reset_host_t<float>(env, mask_host, obs_host);
+}
+int track2d_reset_host_u8(track2d_env *env, const uint8_t *mask_host, uint8_t *obs_host) {
+    T2D_REQUIRE(env, "null handle");
+    DeviceGuard guard(env->cfg.device);
+    return reset_host_t<uint8_t>(env, mask_host, obs_host);
+}
+int track2d_step_host(track2d_env *env, const int32_t *actions_host, float *obs_host, float *reward_host, uint8_t *done_host) {
+    T2D_REQUIRE(env, "null handle");
+    T2D_REQUIRE(actions_host, "step_host: actions required");
+    DeviceGuard guard(env->cfg.device);
+    return step_host_t<float>(env, actions_host, obs_host, reward_host, done_host);
+}
+int track2d_step_host_u8(track2d_env *env, const int32_t *actions_host, uint8_t *obs_host, float *reward_host, uint8_t *done_host) {
+    T2D_REQUIRE(env, "null handle");
+    T2D_REQUIRE(actions_host, "step_host_u8: actions required");
+    DeviceGuard guard(env->cfg.device);
+    return step_host_t<uint8_t>(env, actions_host, obs_host, reward_host, done_host);
 }
 
 // ---- state read-back / injection ---------------------------------------------------------------------

@@ -114,22 +114,24 @@ class Track2DVecEnv(object):
         _lib.check(self.lib.track2d_init_maze(self.h, _ptr(mask), self._stream()), self.lib)
 
     # ---- host-buffer API -----------------------------------------------------------------------
-    def alloc_host_buffers(self):
-        """pinned host buffers for step_host / reset_host"""
+    def alloc_host_buffers(self, obs_dtype=torch.float32):
+        """pinned host buffers for step_host / reset_host (obs_dtype uint8: the quarter-traffic variant)"""
         E = self.num_envs
         hw = tuple(self.obs.shape[1:])
         return dict(actions=torch.zeros((E, 2), dtype=torch.int32).pin_memory(),
-                    obs=torch.zeros((E,) + hw, dtype=torch.float32).pin_memory(),
+                    obs=torch.zeros((E,) + hw, dtype=obs_dtype).pin_memory(),
                     reward=torch.zeros((E, 2), dtype=torch.float32).pin_memory(),
                     done=torch.zeros((E,), dtype=torch.uint8).pin_memory())
 
     def reset_host(self, obs_host, mask_host=None):
-        _lib.check(self.lib.track2d_reset_host(self.h, _ptr(mask_host), _ptr(obs_host)), self.lib)
+        fn = self.lib.track2d_reset_host if obs_host.dtype == torch.float32 else self.lib.track2d_reset_host_u8
+        _lib.check(fn(self.h, _ptr(mask_host), _ptr(obs_host)), self.lib)
         return obs_host
 
     def step_host(self, actions_host, obs_host, reward_host, done_host):
         """numpy-facing step: host actions in, host obs/reward/done out (H2D + kernels + D2H inside)."""
-        _lib.check(self.lib.track2d_step_host(self.h, _ptr(actions_host), _ptr(obs_host), _ptr(reward_host), _ptr(done_host)), self.lib)
+        fn = self.lib.track2d_step_host if obs_host.dtype == torch.float32 else self.lib.track2d_step_host_u8
+        _lib.check(fn(self.h, _ptr(actions_host), _ptr(obs_host), _ptr(reward_host), _ptr(done_host)), self.lib)
         return obs_host, reward_host, done_host
 
     # ---- state read-back / injection (synchronous; tests and the single-env shim) ----------------

@@ -106,7 +106,13 @@ class Agent(object):
             self.env.step_host(host['actions'], host['obs'], host['reward'], host['done'])
             # H2D from pinned memory.  Through .data: the rollout slots share one allocation (one autograd version
             # counter) and slot t is already saved for backward when slot t + 1 is filled.
-            self.obs_buf.data[t + 1].copy_(host['obs'], non_blocking=True)
+            if host['obs'].dtype == torch.uint8:  # upload a quarter of the bytes, widen to float32 on the device
+                if getattr(self, '_obs_u8', None) is None:
+                    self._obs_u8 = torch.empty(host['obs'].shape, dtype=torch.uint8, device=self.device)
+                self._obs_u8.copy_(host['obs'], non_blocking=True)
+                self.obs_buf.data[t + 1].copy_(self._obs_u8)
+            else:
+                self.obs_buf.data[t + 1].copy_(host['obs'], non_blocking=True)
             self.rew_buf.data[t].copy_(host['reward'], non_blocking=True)
             self.done_buf.data[t].copy_(host['done'], non_blocking=True)
         self.reward = self.rew_buf[t]

@@ -297,7 +297,7 @@ def run_gpu_arm(a):
     value = E * T * world / (ms_per_step * 1e-3)
 
     # ---- e2e: every env.step through the host-buffer C ABI ------------------------------------------------
-    host = tr.env.alloc_host_buffers()
+    host = tr.env.alloc_host_buffers(obs_dtype=torch.uint8 if a.e2e_obs == "u8" else torch.float32)
     k2 = max(1, min(a.steps, a.e2e_steps))
     tr.iteration(host=host)
     barrier()
@@ -308,11 +308,13 @@ def run_gpu_arm(a):
     barrier()
     ms2 = max_over_ranks(e0.elapsed_time(e1)) / k2
     obs_b = E * 2 * 169 * 4
-    h2d = T * (E * 2 * 4 + obs_b + E * 2 * 4 + E)      # actions into the env; obs, reward, done back to the policy's device
-    d2h = T * (E * 2 * 4 + obs_b + E * 2 * 4 + E) + 16  # actions out of the policy; obs, reward, done out of the env; loss scalars
+    obs_pcie = E * 2 * 169 * (1 if a.e2e_obs == "u8" else 4)
+    h2d = T * (E * 2 * 4 + obs_pcie + E * 2 * 4 + E)      # actions into the env; obs, reward, done back to the policy's device
+    d2h = T * (E * 2 * 4 + obs_pcie + E * 2 * 4 + E) + 16  # actions out of the policy; obs, reward, done out of the env; loss scalars
     e2e = {"value": E * T * world / (ms2 * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "ms_per_step": ms2, "steps": k2,
-           "what": "Agent.action_train with env.step via track2d_step_host (pinned host buffers) and the observation re-uploaded, per GPU"}
+           "what": "Agent.action_train with env.step via track2d_step_host%s (pinned host buffers, %s observations on the host side) "
+                   "and the observation re-uploaded, per GPU" % ("_u8" if a.e2e_obs == "u8" else "", "uint8" if a.e2e_obs == "u8" else "float32")}
     status = tr.env.status()
     replicas_identical = None
     if world > 1:  # every rank applied the same fused update to the same all-reduced gradient: the weights must be bit-identical
@@ -347,6 +349,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-obs", default="u8", choices=["u8", "f32"], help="dtype of the observations in the host buffers of the e2e path")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fp32-emulation", action="store_true",
                     help="route the policy's fp32 GEMMs through cuBLAS 12.9 BF16x9 emulation (fp32-accurate, tensor cores); off = SIMT SGEMM")

@@ -129,6 +129,9 @@ int track2d_reset_u8(track2d_env *env, const uint8_t *mask_dev, uint8_t *obs_dev
 /* ---- host-buffer API (what a numpy-facing gym user calls; H2D/D2H inside) -------------------- */
 int track2d_reset_host(track2d_env *env, const uint8_t *mask_host, float *obs_host);
 int track2d_step_host(track2d_env *env, const int32_t *actions_host, float *obs_host, float *reward_host, uint8_t *done_host);
+/* the same with uint8 observations (values 0,1,2,4): a quarter of the PCIe traffic; the consumer converts after upload */
+int track2d_reset_host_u8(track2d_env *env, const uint8_t *mask_host, uint8_t *obs_host);
+int track2d_step_host_u8(track2d_env *env, const int32_t *actions_host, uint8_t *obs_host, float *reward_host, uint8_t *done_host);
 
 /* ---- state read-back / injection (host pointers, synchronous; parity tests and the gym shim) -- */
 

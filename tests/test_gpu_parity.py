@@ -336,11 +336,13 @@ def test_uint8_observations_equal_float32(t2d):
     b.close()
 
 
-def test_host_buffer_api_equals_device_api(t2d):
+@pytest.mark.parametrize("host_dtype", [torch.float32, torch.uint8])
+def test_host_buffer_api_equals_device_api(t2d, host_dtype):
     E = 515
     a = t2d.Track2DVecEnv("Track2D-BlockPartialRam-v0", num_envs=E, seed=2, rng="philox", auto_reset=True)
     b = t2d.Track2DVecEnv("Track2D-BlockPartialRam-v0", num_envs=E, seed=2, rng="philox", auto_reset=True)
-    hb = b.alloc_host_buffers()
+    hb = b.alloc_host_buffers(obs_dtype=host_dtype)
+    assert hb["obs"].dtype == host_dtype
     oa = a.reset()
     b.reset_host(hb["obs"])
     assert (oa.cpu() == hb["obs"]).all()
