@@ -1,0 +1,453 @@
+// track2d_gemm.cu -- float32-accurate GEMM on the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulators in
+// TMEM) for the policy's fully-connected and LSTM layers (model.py:116-127,175-182, perception.py:73,89-91 of the
+// reference run them as float32 on the CPU; the cuBLAS fp32 path on B200 is a SIMT kernel and was 52 % of the
+// rollout+update step, profiles/).
+//
+//     D[m][n] = epilogue( sum_k A(m,k) * B(n,k) ),        m < M, n < N, k < K
+//
+// 3xTF32: every fp32 operand is split on the fly into x = hi + lo with hi, lo representable in TF32 (11 significant bits
+// each; the remainder is below 2^-22 |x|), and each reduction block issues three MMAs into the same fp32 accumulator,
+//     D += A_lo*B_hi ; D += A_hi*B_lo ; D += A_hi*B_hi,
+// dropping only the lo*lo term (2^-22 relative).  The products of TF32 values are exact and the accumulation is fp32, so
+// the result carries fp32 accuracy -- unlike plain TF32, which loses 13 mantissa bits of every input.
+//
+// Structure (one persistent CTA per SM, 13 warps, warp-specialised):
+//   warps 5..12  producers   coalesced 16-byte global loads (two reduction blocks prefetched in registers), hi/lo split,
+//                            st.shared into the UMMA canonical SWIZZLE_128B layout (K-major or MN-major, so the same
+//                            kernel runs y = x W^T, dx = dy W and dW = dy^T x without any transposed copy),
+//                            fence.proxy.async + mbarrier arrive
+//   warp 4       MMA issuer  one lane issues 12 tcgen05.mma (128 x 128 x 8) per 32-deep reduction block; tcgen05.commit
+//                            releases the shared-memory stage / publishes the accumulator
+//   warps 0..3   epilogue    tcgen05.ld (32 lanes x 32 columns per warp), + bias, ReLU, 16-byte global stores; the
+//                            accumulator is double-buffered in TMEM (2 x 128 columns) so it overlaps the next tile
+// Three 64 KB shared-memory stages (A_hi, A_lo, B_hi, B_lo tiles of 128 x 32 floats).  Split-K (weight gradients: the
+// reduction runs over the env axis) writes partial tiles to a workspace; a second kernel sums them in a fixed order, so
+// results are bit-reproducible run to run.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/track2d.h"
+
+void t2d_set_error(const char *fmt, ...);
+void t2d_count_launches(int n);
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 32;
+constexpr int STAGES = 3;
+constexpr int TILE_BYTES = BM * BK * 4;      // 16 KB; BM == BN
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;  // A_hi | A_lo | B_hi | B_lo
+constexpr int EPI_WARPS = 4, MMA_WARP = 4, PROD_WARP0 = 5, PROD_WARPS = 8;
+constexpr int THREADS = (EPI_WARPS + 1 + PROD_WARPS) * 32;  // 416
+constexpr int PROD_THREADS = PROD_WARPS * 32;               // 256
+constexpr int TMEM_COLS = 2 * BN;                           // two accumulator buffers
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 128 /* barriers */;
+
+struct GemmParams {
+    const float *A, *B;
+    float *D;           // splits == 1: the output; else the partial-tile workspace [splits][M][N]
+    const float *bias;  // [N] or null (applied here only when splits == 1)
+    long long lda, ldb, ldd, split_stride;
+    int M, N, K;
+    int tiles_m, tiles_n, splits, nkb;  // nkb = ceil(K / BK)
+    int relu;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    for (uint32_t spins = 0;; ++spins) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if (spins > (1u << 24)) {  // a lost arrival must not hang the device: fail the launch instead
+            printf("track2d_gemm: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory matrix descriptor.  Bits: [0,14) start address >> 4, [16,30) leading-dimension byte offset >> 4,
+// [32,46) stride-dimension byte offset >> 4, [46,48) descriptor version (1 on sm_100), [61,64) layout type
+// (2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+           (1ull << 46) | ((uint64_t)layout_type << 61);
+}
+// Canonical layouts of one 128 (rows of M or N) x 32 (reduction) fp32 operand tile, 16 KB:
+//   K-major  (reduction index contiguous in global memory), SWIZZLE_128B: row r, 16-byte chunk c of its 128-byte line at
+//            (r/8)*1024 + (r%8)*128 + ((c ^ r%8) * 16);  LBO unused, SBO = 1024; the k-th 8-deep MMA starts 32*k bytes in
+//   MN-major (row index contiguous), SWIZZLE_128B_BASE32B -- the only MN-major layout the tensor core takes for 32-bit
+//            operands: atoms of 32 rows x 4 reduction indices (4 lines of 128 bytes) whose 32-byte chunks are XOR-ed with
+//            the line number.  Reduction index kk, 16-byte row chunk c32 (of 32) at
+//            (kk/4)*2048 + (c32/8)*512 + (kk%4)*128 + (((c32%8)/2 ^ kk%4) * 32) + (c32%2)*16;  LBO = 512 (next 32 rows),
+//            SBO = 2048 (next 4 reduction indices); the k-th 8-deep MMA starts 4096*k bytes in
+template <bool MN>
+__device__ __forceinline__ uint64_t tile_desc(uint32_t saddr, int k8) {
+    return MN ? umma_desc(saddr + 4096u * k8, 512u, 2048u, 1u) : umma_desc(saddr + 32u * k8, 16u, 1024u, 2u);
+}
+template <bool MN>
+__device__ __forceinline__ uint32_t tile_offset(int pt, int i) {
+    if (!MN) {
+        const int row = (pt >> 3) + 32 * i, c = pt & 7;
+        return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((c ^ (row & 7)) << 4));
+    } else {
+        const int kk = (pt >> 5) + 8 * i, c32 = pt & 31, kr = kk & 3, c = c32 & 7;
+        return (uint32_t)((kk >> 2) * 2048 + (c32 >> 3) * 512 + kr * 128 + ((((c >> 1) ^ kr) << 5) | ((c & 1) << 4)));
+    }
+}
+
+// x = hi + lo, both with at most 11 significant bits (TF32); round to nearest so |x - hi - lo| <= 2^-22 |x|
+__device__ __forceinline__ void split1(float x, float &hi, float &lo) {
+    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+    const float r = x - hi;  // exact
+    lo = __uint_as_float((__float_as_uint(r) + 0x1000u) & 0xFFFFE000u);
+}
+
+struct Cursor {  // walks this CTA's (work item, reduction block) sequence
+    int item, kb, kb_end, m0, n0;
+    __device__ __forceinline__ void set_item(const GemmParams &p, int it, int n_items) {
+        item = it;
+        if (it >= n_items) return;
+        const int tn = it % p.tiles_n, tm = (it / p.tiles_n) % p.tiles_m, sp = it / (p.tiles_n * p.tiles_m);
+        m0 = tm * BM;
+        n0 = tn * BN;
+        kb = (int)((long long)p.nkb * sp / p.splits);
+        kb_end = (int)((long long)p.nkb * (sp + 1) / p.splits);
+    }
+};
+
+template <bool MN>
+__device__ __forceinline__ void load_tile(float4 (&r)[4], const float *__restrict__ X, long long ld, int mn0, int k0, int mn_lim,
+                                          int k_lim, int pt) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int mn, k;
+        long long off;
+        if (!MN) {
+            mn = mn0 + (pt >> 3) + 32 * i;
+            k = k0 + (pt & 7) * 4;
+            off = (long long)mn * ld + k;
+        } else {
+            k = k0 + (pt >> 5) + 8 * i;
+            mn = mn0 + (pt & 31) * 4;
+            off = (long long)k * ld + mn;
+        }
+        r[i] = (mn < mn_lim && k < k_lim) ? __ldg(reinterpret_cast<const float4 *>(X + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+template <bool MN>
+__device__ __forceinline__ void store_tile(uint32_t hi_base, uint32_t lo_base, const float4 (&r)[4], int pt) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float4 h, l;
+        split1(r[i].x, h.x, l.x);
+        split1(r[i].y, h.y, l.y);
+        split1(r[i].z, h.z, l.z);
+        split1(r[i].w, h.w, l.w);
+        const uint32_t off = tile_offset<MN>(pt, i);
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(hi_base + off), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(lo_base + off), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
+    }
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
+    const uint32_t bars = smem0 + STAGES * STAGE_BYTES;
+    // barriers: full[STAGES], empty[STAGES], acc_full[2], acc_empty[2]; then the TMEM base address
+    const uint32_t bar_full = bars, bar_empty = bars + 8 * STAGES, bar_accf = bars + 16 * STAGES, bar_acce = bar_accf + 16;
+    const uint32_t tmem_slot = bar_acce + 16;
+    uint32_t *tmem_slot_ptr = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_items = p.tiles_m * p.tiles_n * p.splits;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bar_full + 8 * s, PROD_THREADS);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(bar_accf + 8 * a, 1);
+            mbar_init(bar_acce + 8 * a, EPI_WARPS * 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == MMA_WARP) {  // this warp owns the TMEM allocation (and frees it at the end)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp >= PROD_WARP0) {
+        // ===== producers =====
+        const int pt = threadIdx.x - PROD_WARP0 * 32;
+        float4 a[3][4], b[3][4];
+        Cursor lc;
+        lc.set_item(p, blockIdx.x, n_items);
+        int n_loaded = 0;
+        auto issue = [&](float4 (&ra)[4], float4 (&rb)[4]) {
+            load_tile<A_MN>(ra, p.A, p.lda, lc.m0, lc.kb * BK, p.M, p.K, pt);
+            load_tile<B_MN>(rb, p.B, p.ldb, lc.n0, lc.kb * BK, p.N, p.K, pt);
+            ++n_loaded;
+            if (++lc.kb == lc.kb_end) lc.set_item(p, lc.item + gridDim.x, n_items);
+        };
+        if (lc.item < n_items) issue(a[0], b[0]);
+        if (lc.item < n_items) issue(a[1], b[1]);
+        int it = 0;
+        while (it < n_loaded) {
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+                if (it < n_loaded) {
+                    if (lc.item < n_items) issue(a[(u + 2) % 3], b[(u + 2) % 3]);
+                    const int s = it % STAGES;
+                    mbar_wait(bar_empty + 8 * s, ((it / STAGES) & 1) ^ 1);
+                    const uint32_t st = smem0 + s * STAGE_BYTES;
+                    store_tile<A_MN>(st, st + TILE_BYTES, a[u], pt);
+                    store_tile<B_MN>(st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, b[u], pt);
+                    fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
+                    mbar_arrive(bar_full + 8 * s);
+                    ++it;
+                }
+            }
+        }
+    } else if (warp == MMA_WARP) {
+        // ===== MMA issuer =====
+        // instruction descriptor: D fp32 (bits 4-5 = 1), A and B TF32 (bits 7-9, 10-12 = 2), major-ness of A / B (bits 15, 16;
+        // 1 = MN-major), N >> 3 (bits 17-22), M >> 4 (bits 24-28)
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                               ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        int it = 0, t = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++t) {
+            const int sp = item / (p.tiles_n * p.tiles_m);
+            const int kb0 = (int)((long long)p.nkb * sp / p.splits), kb1 = (int)((long long)p.nkb * (sp + 1) / p.splits);
+            const int acc = t & 1;
+            mbar_wait(bar_acce + 8 * acc, ((t >> 1) & 1) ^ 1);  // epilogue has drained this accumulator buffer
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+            for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                const int s = it % STAGES;
+                mbar_wait(bar_full + 8 * s, (it / STAGES) & 1);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t st = smem0 + s * STAGE_BYTES;
+#pragma unroll
+                    for (int k8 = 0; k8 < BK / 8; ++k8) {
+                        const uint64_t a_hi = tile_desc<A_MN>(st, k8), a_lo = tile_desc<A_MN>(st + TILE_BYTES, k8);
+                        const uint64_t b_hi = tile_desc<B_MN>(st + 2 * TILE_BYTES, k8), b_lo = tile_desc<B_MN>(st + 3 * TILE_BYTES, k8);
+                        tc_mma_tf32(d_tmem, a_lo, b_hi, idesc, (kb > kb0 || k8 > 0) ? 1u : 0u);
+                        tc_mma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
+                        tc_mma_tf32(d_tmem, a_hi, b_hi, idesc, 1u);
+                    }
+                    tc_commit(bar_empty + 8 * s);                     // stage free once these MMAs have read it
+                    if (kb == kb1 - 1) tc_commit(bar_accf + 8 * acc);  // accumulator complete
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ===== epilogue: warp w owns TMEM lanes [32w, 32w + 32) = tile rows =====
+        int t = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++t) {
+            const int tn = item % p.tiles_n, tm = (item / p.tiles_n) % p.tiles_m, sp = item / (p.tiles_n * p.tiles_m);
+            const int acc = t & 1;
+            mbar_wait(bar_accf + 8 * acc, (t >> 1) & 1);
+            tc_fence_after();
+            const int row = tm * BM + warp * 32 + lane;
+            float *drow = p.D + (long long)sp * p.split_stride + (long long)row * p.ldd;
+            const bool fused = p.splits == 1;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t r[32];
+                tc_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN + c * 32), r);
+                tc_wait_ld();
+                const int col0 = tn * BN + c * 32;
+                if (row < p.M) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int col = col0 + 4 * q;
+                        if (col < p.N) {
+                            float4 v = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
+                                                   __uint_as_float(r[4 * q + 3]));
+                            if (fused) {
+                                if (p.bias) {
+                                    const float4 bv = __ldg(reinterpret_cast<const float4 *>(p.bias + col));
+                                    v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+                                }
+                                if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                            }
+                            *reinterpret_cast<float4 *>(drow + col) = v;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(bar_acce + 8 * acc);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == MMA_WARP) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+    }
+}
+
+// D[m][n] = epilogue( sum_s part[s][m][n] ), fixed summation order
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float *__restrict__ part, long long split_stride, int splits, float *__restrict__ D,
+                                                            long long ldd, int M, int N, const float *__restrict__ bias, int relu) {
+    const int n4 = N >> 2;
+    const long long total = (long long)M * n4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int m = (int)(i / n4), n = (int)(i % n4) * 4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s = 0; s < splits; ++s) {
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(part + (long long)s * split_stride + (long long)m * N + n));
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        if (bias) {
+            const float4 bv = __ldg(reinterpret_cast<const float4 *>(bias + n));
+            acc.x += bv.x; acc.y += bv.y; acc.z += bv.z; acc.w += bv.w;
+        }
+        if (relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+        *reinterpret_cast<float4 *>(D + (long long)m * ldd + n) = acc;
+    }
+}
+
+int g_sm_count = 0;
+
+template <bool A_MN, bool B_MN>
+cudaError_t launch(const GemmParams &p, int grid, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    gemm_tf32x3_kernel<A_MN, B_MN><<<grid, THREADS, SMEM_BYTES, st>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+extern "C" int64_t track2d_gemm_workspace_floats(int64_t M, int64_t N, int64_t K) {
+    // upper bound over the split counts track2d_gemm_tf32x3 may choose
+    const int64_t tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    const int64_t nkb = (K + BK - 1) / BK;
+    int64_t splits = tiles >= 96 ? 1 : (148 + tiles - 1) / tiles;
+    if (splits > nkb) splits = nkb;
+    return splits <= 1 ? 0 : splits * M * N;
+}
+
+extern "C" int track2d_gemm_tf32x3(const float *a_dev, int a_mn_major, int64_t lda, const float *b_dev, int b_mn_major, int64_t ldb,
+                                   float *d_dev, int64_t ldd, int64_t M, int64_t N, int64_t K, const float *bias_dev, int relu,
+                                   float *workspace_dev, int64_t workspace_floats, void *stream) {
+    if (!a_dev || !b_dev || !d_dev || M <= 0 || N <= 0 || K <= 0 || M > (1ll << 30) || N > (1ll << 30) || K > (1ll << 30)) {
+        t2d_set_error("track2d_gemm_tf32x3: bad argument");
+        return T2D_E_INVALID;
+    }
+    // 16-byte vector access everywhere: the contiguous extent of every operand and all leading dimensions are multiples of 4
+    const bool ok_a = a_mn_major ? (M % 4 == 0) : (K % 4 == 0), ok_b = b_mn_major ? (N % 4 == 0) : (K % 4 == 0);
+    if (!ok_a || !ok_b || N % 4 || lda % 4 || ldb % 4 || ldd % 4 || ((uintptr_t)a_dev | (uintptr_t)b_dev | (uintptr_t)d_dev | (uintptr_t)bias_dev) % 16) {
+        t2d_set_error("track2d_gemm_tf32x3: operands must be 16-byte aligned with extents / leading dimensions that are multiples of 4");
+        return T2D_E_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (g_sm_count == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || g_sm_count <= 0) {
+            t2d_set_error("track2d_gemm_tf32x3: cannot query the device");
+            g_sm_count = 0;
+            return T2D_E_CUDA;
+        }
+    }
+    GemmParams p;
+    p.A = a_dev; p.B = b_dev; p.bias = bias_dev;
+    p.lda = lda; p.ldb = ldb;
+    p.M = (int)M; p.N = (int)N; p.K = (int)K;
+    p.tiles_m = (int)((M + BM - 1) / BM);
+    p.tiles_n = (int)((N + BN - 1) / BN);
+    p.nkb = (int)((K + BK - 1) / BK);
+    p.relu = relu;
+    const int64_t tiles = (int64_t)p.tiles_m * p.tiles_n;
+    int64_t splits = tiles >= 96 ? 1 : (148 + tiles - 1) / tiles;  // fill the SMs when there are few output tiles (weight gradients)
+    if (splits > p.nkb) splits = p.nkb;
+    if (splits > 1 && (!workspace_dev || workspace_floats < splits * M * N || (uintptr_t)workspace_dev % 16)) {
+        t2d_set_error("track2d_gemm_tf32x3: split-K needs a workspace of %lld floats (track2d_gemm_workspace_floats)", (long long)(splits * M * N));
+        return T2D_E_INVALID;
+    }
+    p.splits = (int)splits;
+    if (splits > 1) { p.D = workspace_dev; p.ldd = N; p.split_stride = M * N; }
+    else { p.D = d_dev; p.ldd = ldd; p.split_stride = 0; }
+    const int64_t items = tiles * splits;
+    const int grid = (int)(items < g_sm_count ? items : g_sm_count);
+    cudaError_t e;
+    if (a_mn_major) e = b_mn_major ? launch<true, true>(p, grid, st) : launch<true, false>(p, grid, st);
+    else e = b_mn_major ? launch<false, true>(p, grid, st) : launch<false, false>(p, grid, st);
+    if (e != cudaSuccess) {
+        t2d_set_error("track2d_gemm_tf32x3: launch failed: %s", cudaGetErrorString(e));
+        return T2D_E_CUDA;
+    }
+    t2d_count_launches(1);
+    if (splits > 1) {
+        const long long total = M * (N / 4);
+        int blocks = (int)((total + 255) / 256);
+        if (blocks > g_sm_count * 8) blocks = g_sm_count * 8;
+        splitk_reduce_kernel<<<blocks, 256, 0, st>>>(workspace_dev, M * N, (int)splits, d_dev, ldd, (int)M, (int)N, bias_dev, relu);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            t2d_set_error("track2d_gemm_tf32x3: reduce launch failed: %s", cudaGetErrorString(e));
+            return T2D_E_CUDA;
+        }
+        t2d_count_launches(1);
+    }
+    return T2D_OK;
+}

@@ -195,6 +195,20 @@ int track2d_maze_conv_backward(const float *x_dev, const float *y2_dev, const fl
                                const float *b1_dev, const float *w2_dev, float *dw1_dev, float *db1_dev, float *dw2_dev, float *db2_dev,
                                void *stream);
 
+/* float32-accurate GEMM on the tcgen05 tensor cores (3xTF32 split, fp32 accumulation in TMEM) for the policy's Linear /
+ * LSTMCell layers (reference: nn.Linear / nn.LSTMCell in model.py:116-127,175-182, perception.py:73 -- fp32 on the CPU):
+ *     D[m][n] = act( sum_k A(m,k) * B(n,k) + bias[n] ),  m < M, n < N, k < K;  D row-major with leading dimension ldd.
+ * A(m,k) is read at a_dev[m*lda + k] (a_mn_major == 0, "K-major") or a_dev[k*lda + m] (a_mn_major == 1); B(n,k) likewise at
+ * b_dev[n*ldb + k] or b_dev[k*ldb + n].  So y = x W^T is (A=x K-major, B=W K-major), dx = dy W is (A=dy K-major, B=W MN-major)
+ * and dW = dy^T x is (A=dy MN-major, B=x MN-major, K = batch) with no transposed copies.  bias_dev may be NULL; relu != 0 applies
+ * max(., 0).  All pointers are device pointers, 16-byte aligned; contiguous extents and leading dimensions are multiples of 4.
+ * When few output tiles exist the reduction is split across SMs: pass a workspace of track2d_gemm_workspace_floats(M, N, K)
+ * floats (0 = none needed).  The partial sums are combined in a fixed order (bit-reproducible). */
+int64_t track2d_gemm_workspace_floats(int64_t M, int64_t N, int64_t K);
+int track2d_gemm_tf32x3(const float *a_dev, int a_mn_major, int64_t lda, const float *b_dev, int b_mn_major, int64_t ldb,
+                        float *d_dev, int64_t ldd, int64_t M, int64_t N, int64_t K, const float *bias_dev, int relu,
+                        float *workspace_dev, int64_t workspace_floats, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
