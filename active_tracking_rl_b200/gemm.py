@@ -49,7 +49,7 @@ def gemm(a, a_mn_major, lda, b, b_mn_major, ldb, M, N, K, bias=None, relu=False,
 
 def supported(x, weight):
     """shapes / layouts the tensor-core path takes"""
-    return (x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32 and x.dim() == 2 and x.shape[0] % 4 == 0
+    return (x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32 and x.dim() == 2
             and weight.shape[0] % 4 == 0 and weight.shape[1] % 4 == 0 and x.stride(1) == 1 and x.stride(0) % 4 == 0
             and weight.is_contiguous() and x.data_ptr() % 16 == 0 and weight.data_ptr() % 16 == 0)
 
@@ -70,7 +70,7 @@ class _Linear(torch.autograd.Function):
         M, K = x.shape
         N = weight.shape[0]
         if ctx.relu:
-            gy = gy * (y > 0)
+            gy = torch.ops.aten.threshold_backward(gy, y, 0.0)
         gy = gy.contiguous()
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:

@@ -97,6 +97,28 @@ class _MazeConvStack(torch.autograd.Function):
 # "fused": the hand-written conv-stack kernels (CUDA tensors); "gemm_backward": cuDNN forward + im2col/SGEMM backward;
 # "cudnn": plain F.conv2d autograd.  CPU tensors (tests of the host-side logic) always take the F.conv2d route.
 CONV_IMPL = "fused"
+# "tf32x3": the fc / LSTM GEMMs (forward, dgrad, wgrad) run on the tcgen05 tensor cores with fp32 accuracy
+# (csrc/track2d_gemm.cu, 3xTF32 split); "cublas": torch's own fp32 linear (SIMT SGEMM).  CPU tensors always take torch's.
+GEMM_IMPL = "tf32x3"
+
+
+def _linear(x, lin, relu=False):
+    if GEMM_IMPL == "tf32x3" and x.is_cuda:
+        from . import gemm
+        return gemm.linear(x, lin.weight, lin.bias, relu)
+    y = lin(x)
+    return F.relu(y) if relu else y
+
+
+def _lstm_cell(lstm, x, hx, cx):
+    """nn.LSTMCell.forward (model.py:116 `self.lstm(feature, (hx, cx))`): two gate GEMMs + the fused pointwise cell"""
+    if GEMM_IMPL == "tf32x3" and x.is_cuda:
+        from . import gemm
+        igates = gemm.linear(x, lstm.weight_ih)
+        hgates = gemm.linear(hx, lstm.weight_hh)
+        hy, cy, _ = torch.ops.aten._thnn_fused_lstm_cell(igates, hgates, cx, lstm.bias_ih, lstm.bias_hh)
+        return hy, cy
+    return lstm(x, (hx, cx))
 
 
 def weights_init(m):
@@ -144,7 +166,7 @@ class CNN_maze(nn.Module):
         else:
             y = F.relu(self.conv1(y))
             y = F.relu(self.conv2(y))
-        return F.relu(self.fc(y.reshape(B, -1)))
+        return _linear(y.reshape(B, -1), self.fc, relu=True)
 
 
 class PolicyNet(nn.Module):
@@ -196,7 +218,7 @@ class A3C(nn.Module):
 
     def forward(self, x, hx, cx, test=False, forced=None):
         feature = self.encoder(x)
-        hx, cx = self.lstm(feature, (hx, cx))
+        hx, cx = _lstm_cell(self.lstm, feature, hx, cx)
         value = self.critic(hx)
         action, entropy, log_prob = sample_action(self.actor(hx), test, forced)
         return value, action, entropy, log_prob, hx, cx
@@ -221,7 +243,7 @@ class TAT(nn.Module):
 
     def forward(self, x, hx, cx, action_tracker_onehot, test=False, forced=None):
         feature = self.encoder(x) + self.fc_action_tracker(action_tracker_onehot)
-        hx, cx = self.lstm(feature, (hx, cx))
+        hx, cx = _lstm_cell(self.lstm, feature, hx, cx)
         value = self.critic(hx)
         action, entropy, log_prob = sample_action(self.actor(hx), test, forced)
         return value, action, entropy, log_prob, hx, cx, self.reward_aux(hx)
