@@ -11,8 +11,8 @@
 // dropping only the lo*lo term (2^-22 relative).  The products of TF32 values are exact and the accumulation is fp32, so
 // the result carries fp32 accuracy -- unlike plain TF32, which loses 13 mantissa bits of every input.
 //
-// Structure (one persistent CTA per SM, 13 warps, warp-specialised):
-//   warps 5..12  producers   coalesced 16-byte global loads (two reduction blocks prefetched in registers), hi/lo split,
+// Structure (one persistent CTA per SM, 21 warps, warp-specialised):
+//   warps 5..20  producers   coalesced 16-byte global loads (two reduction blocks prefetched in registers), hi/lo split,
 //                            st.shared into the UMMA canonical SWIZZLE_128B layout (K-major or MN-major, so the same
 //                            kernel runs y = x W^T, dx = dy W and dW = dy^T x without any transposed copy),
 //                            fence.proxy.async + mbarrier arrive
@@ -25,7 +25,6 @@
 // results are bit-reproducible run to run.
 #include <cuda_runtime.h>
 #include <stdint.h>
-#include <stdio.h>
 
 #include "../../include/track2d.h"
 
@@ -38,9 +37,10 @@ constexpr int BM = 128, BN = 128, BK = 32;
 constexpr int STAGES = 3;
 constexpr int TILE_BYTES = BM * BK * 4;      // 16 KB; BM == BN
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;  // A_hi | A_lo | B_hi | B_lo
-constexpr int EPI_WARPS = 4, MMA_WARP = 4, PROD_WARP0 = 5, PROD_WARPS = 8;
-constexpr int THREADS = (EPI_WARPS + 1 + PROD_WARPS) * 32;  // 416
-constexpr int PROD_THREADS = PROD_WARPS * 32;               // 256
+constexpr int EPI_WARPS = 4, MMA_WARP = 4, PROD_WARP0 = 5, PROD_WARPS = 16;
+constexpr int THREADS = (EPI_WARPS + 1 + PROD_WARPS) * 32;  // 672
+constexpr int PROD_THREADS = PROD_WARPS * 32;               // 512
+constexpr int NCH = BM * BK / 4 / PROD_THREADS;             // 16-byte chunks per producer thread per operand tile (2)
 constexpr int TMEM_COLS = 2 * BN;                           // two accumulator buffers
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 128 /* barriers */;
 
@@ -74,10 +74,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "r"(bar), "r"(parity)
             : "memory");
         if (ok) return;
-        if (spins > (1u << 24)) {  // a lost arrival must not hang the device: fail the launch instead
-            printf("track2d_gemm: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
-            __trap();
-        }
+        if (spins > (1u << 24)) __trap();  // a lost arrival must not hang the device: fail the launch instead
+    }
+}
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {  // long waits (epilogue): do not steal issue slots
+    uint32_t ok = 0;
+    for (uint32_t spins = 0;; ++spins) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) return;
+        __nanosleep(100);
+        if (spins > (1u << 22)) __trap();
     }
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -130,58 +142,64 @@ __device__ __forceinline__ uint64_t tile_desc(uint32_t saddr, int k8) {
 template <bool MN>
 __device__ __forceinline__ uint32_t tile_offset(int pt, int i) {
     if (!MN) {
-        const int row = (pt >> 3) + 32 * i, c = pt & 7;
+        const int row = (pt >> 3) + (PROD_THREADS / 8) * i, c = pt & 7;
         return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((c ^ (row & 7)) << 4));
     } else {
-        const int kk = (pt >> 5) + 8 * i, c32 = pt & 31, kr = kk & 3, c = c32 & 7;
+        const int kk = (pt >> 5) + (PROD_THREADS / 32) * i, c32 = pt & 31, kr = kk & 3, c = c32 & 7;
         return (uint32_t)((kk >> 2) * 2048 + (c32 >> 3) * 512 + kr * 128 + ((((c >> 1) ^ kr) << 5) | ((c & 1) << 4)));
     }
 }
 
-// x = hi + lo, both with at most 11 significant bits (TF32); round to nearest so |x - hi - lo| <= 2^-22 |x|
+// x = hi + lo: hi = x rounded to TF32 (11 significant bits, cvt.rna), lo = x - hi exactly (|lo| <= 2^-12 |x|; the tensor core
+// reads its leading 11 bits, so |x - hi - lo_used| <= 2^-23 |x|)
 __device__ __forceinline__ void split1(float x, float &hi, float &lo) {
-    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
-    const float r = x - hi;  // exact
-    lo = __uint_as_float((__float_as_uint(r) + 0x1000u) & 0xFFFFE000u);
+    uint32_t h;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+    hi = __uint_as_float(h & 0xFFFFE000u);
+    lo = x - hi;
 }
 
-struct Cursor {  // walks this CTA's (work item, reduction block) sequence
-    int item, kb, kb_end, m0, n0;
-    __device__ __forceinline__ void set_item(const GemmParams &p, int it, int n_items) {
-        item = it;
-        if (it >= n_items) return;
-        const int tn = it % p.tiles_n, tm = (it / p.tiles_n) % p.tiles_m, sp = it / (p.tiles_n * p.tiles_m);
-        m0 = tm * BM;
-        n0 = tn * BN;
-        kb = (int)((long long)p.nkb * sp / p.splits);
-        kb_end = (int)((long long)p.nkb * (sp + 1) / p.splits);
+// One producer thread's view of an operand: the addresses of its NCH 16-byte chunks in the current reduction block, advanced
+// by a constant stride per block (no per-block index arithmetic)
+template <bool MN>
+struct OperandCursor {
+    const float *ptr;     // chunk 0 of this thread in the current reduction block; chunk i is i * chunk_step further
+    long long chunk_step, block_step;
+    int kofs;             // reduction index of chunk 0 relative to the block start
+    uint32_t ok;          // bit i: chunk i lies inside the operand's M / N extent
+    __device__ __forceinline__ void set_tile(const float *X, long long ld, int mn0, int kb, int mn_lim, int pt) {
+        ok = 0;
+        if (!MN) {
+            const int mn = mn0 + (pt >> 3);
+            kofs = (pt & 7) * 4;
+            chunk_step = (long long)(PROD_THREADS / 8) * ld;
+            block_step = BK;
+            ptr = X + (long long)mn * ld + (long long)kb * BK + kofs;
+#pragma unroll
+            for (int i = 0; i < NCH; ++i) ok |= (mn + (PROD_THREADS / 8) * i < mn_lim ? 1u : 0u) << i;
+        } else {
+            const int mn = mn0 + (pt & 31) * 4;
+            kofs = pt >> 5;
+            chunk_step = (long long)(PROD_THREADS / 32) * ld;
+            block_step = (long long)BK * ld;
+            ptr = X + ((long long)kb * BK + kofs) * ld + mn;
+            ok = mn < mn_lim ? 0xFFFFFFFFu : 0u;
+        }
+    }
+    __device__ __forceinline__ void load(float4 (&r)[NCH], int k0, int k_lim) {
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) {
+            const int k = k0 + kofs + (MN ? (PROD_THREADS / 32) * i : 0);
+            r[i] = (((ok >> i) & 1u) && k < k_lim) ? __ldg(reinterpret_cast<const float4 *>(ptr + i * chunk_step)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        ptr += block_step;
     }
 };
 
 template <bool MN>
-__device__ __forceinline__ void load_tile(float4 (&r)[4], const float *__restrict__ X, long long ld, int mn0, int k0, int mn_lim,
-                                          int k_lim, int pt) {
+__device__ __forceinline__ void store_tile(uint32_t hi_base, uint32_t lo_base, const float4 (&r)[NCH], int pt) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        int mn, k;
-        long long off;
-        if (!MN) {
-            mn = mn0 + (pt >> 3) + 32 * i;
-            k = k0 + (pt & 7) * 4;
-            off = (long long)mn * ld + k;
-        } else {
-            k = k0 + (pt >> 5) + 8 * i;
-            mn = mn0 + (pt & 31) * 4;
-            off = (long long)k * ld + mn;
-        }
-        r[i] = (mn < mn_lim && k < k_lim) ? __ldg(reinterpret_cast<const float4 *>(X + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-}
-
-template <bool MN>
-__device__ __forceinline__ void store_tile(uint32_t hi_base, uint32_t lo_base, const float4 (&r)[4], int pt) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < NCH; ++i) {
         float4 h, l;
         split1(r[i].x, h.x, l.x);
         split1(r[i].y, h.y, l.y);
@@ -229,24 +247,36 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const GemmParam
     if (warp >= PROD_WARP0) {
         // ===== producers =====
         const int pt = threadIdx.x - PROD_WARP0 * 32;
-        float4 a[3][4], b[3][4];
-        Cursor lc;
-        lc.set_item(p, blockIdx.x, n_items);
-        int n_loaded = 0;
-        auto issue = [&](float4 (&ra)[4], float4 (&rb)[4]) {
-            load_tile<A_MN>(ra, p.A, p.lda, lc.m0, lc.kb * BK, p.M, p.K, pt);
-            load_tile<B_MN>(rb, p.B, p.ldb, lc.n0, lc.kb * BK, p.N, p.K, pt);
-            ++n_loaded;
-            if (++lc.kb == lc.kb_end) lc.set_item(p, lc.item + gridDim.x, n_items);
+        float4 a[3][NCH], b[3][NCH];
+        OperandCursor<A_MN> ca;
+        OperandCursor<B_MN> cb;
+        int item = blockIdx.x, kb = 0, kb_end = 0, n_loaded = 0;
+        auto set_item = [&]() {  // this CTA's next work item: (split, tile_m, tile_n) -> reduction-block range and operand cursors
+            if (item >= n_items) return;
+            const int tn = item % p.tiles_n, tm = (item / p.tiles_n) % p.tiles_m, sp = item / (p.tiles_n * p.tiles_m);
+            kb = (int)((long long)p.nkb * sp / p.splits);
+            kb_end = (int)((long long)p.nkb * (sp + 1) / p.splits);
+            ca.set_tile(p.A, p.lda, tm * BM, kb, p.M, pt);
+            cb.set_tile(p.B, p.ldb, tn * BN, kb, p.N, pt);
         };
-        if (lc.item < n_items) issue(a[0], b[0]);
-        if (lc.item < n_items) issue(a[1], b[1]);
+        auto issue = [&](float4 (&ra)[NCH], float4 (&rb)[NCH]) {
+            ca.load(ra, kb * BK, p.K);
+            cb.load(rb, kb * BK, p.K);
+            ++n_loaded;
+            if (++kb == kb_end) {
+                item += gridDim.x;
+                set_item();
+            }
+        };
+        set_item();
+        if (item < n_items) issue(a[0], b[0]);
+        if (item < n_items) issue(a[1], b[1]);
         int it = 0;
         while (it < n_loaded) {
 #pragma unroll
             for (int u = 0; u < 3; ++u) {
                 if (it < n_loaded) {
-                    if (lc.item < n_items) issue(a[(u + 2) % 3], b[(u + 2) % 3]);
+                    if (item < n_items) issue(a[(u + 2) % 3], b[(u + 2) % 3]);  // two reduction blocks ahead
                     const int s = it % STAGES;
                     mbar_wait(bar_empty + 8 * s, ((it / STAGES) & 1) ^ 1);
                     const uint32_t st = smem0 + s * STAGE_BYTES;
@@ -298,7 +328,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const GemmParam
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++t) {
             const int tn = item % p.tiles_n, tm = (item / p.tiles_n) % p.tiles_m, sp = item / (p.tiles_n * p.tiles_m);
             const int acc = t & 1;
-            mbar_wait(bar_accf + 8 * acc, (t >> 1) & 1);
+            mbar_wait_backoff(bar_accf + 8 * acc, (t >> 1) & 1);
             tc_fence_after();
             const int row = tm * BM + warp * 32 + lane;
             float *drow = p.D + (long long)sp * p.split_stride + (long long)row * p.ldd;
