@@ -5,26 +5,30 @@
 //
 //     D[m][n] = epilogue( sum_k A(m,k) * B(n,k) ),        m < M, n < N, k < K
 //
-// 3xTF32: every fp32 operand is split on the fly into x = hi + lo with hi, lo representable in TF32 (11 significant bits
-// each; the remainder is below 2^-22 |x|), and each reduction block issues three MMAs into the same fp32 accumulator,
+// 3xTF32: every fp32 operand is split on the fly into x = hi + lo with hi = x rounded to TF32 and lo = x - hi, and each
+// reduction step issues three MMAs into the same fp32 accumulator,
 //     D += A_lo*B_hi ; D += A_hi*B_lo ; D += A_hi*B_hi,
 // dropping only the lo*lo term (2^-22 relative).  The products of TF32 values are exact and the accumulation is fp32, so
 // the result carries fp32 accuracy -- unlike plain TF32, which loses 13 mantissa bits of every input.
 //
 // Structure (one persistent CTA per SM, 21 warps, warp-specialised):
 //   warps 5..20  producers   coalesced 16-byte global loads (two reduction blocks prefetched in registers), hi/lo split,
-//                            st.shared into the UMMA canonical SWIZZLE_128B layout (K-major or MN-major, so the same
-//                            kernel runs y = x W^T, dx = dy W and dW = dy^T x without any transposed copy),
-//                            fence.proxy.async + mbarrier arrive
-//   warp 4       MMA issuer  one lane issues 12 tcgen05.mma (128 x 128 x 8) per 32-deep reduction block; tcgen05.commit
-//                            releases the shared-memory stage / publishes the accumulator
-//   warps 0..3   epilogue    tcgen05.ld (32 lanes x 32 columns per warp), + bias, ReLU, 16-byte global stores; the
-//                            accumulator is double-buffered in TMEM (2 x 128 columns) so it overlaps the next tile
-// Three 64 KB shared-memory stages (A_hi, A_lo, B_hi, B_lo tiles of 128 x 32 floats).  Split-K (weight gradients: the
-// reduction runs over the env axis) writes partial tiles to a workspace; a second kernel sums them in a fixed order, so
-// results are bit-reproducible run to run.
+//                            st.shared into the UMMA canonical swizzled layouts (K-major or MN-major, so the same kernel
+//                            runs y = x W^T, dx = dy W and dW = dy^T x without any transposed copy), fence.proxy.async +
+//                            mbarrier arrive
+//   warp 4       MMA issuer  one lane issues the tcgen05.mma's (128 x 128 x 8 each); tcgen05.commit releases the
+//                            shared-memory stage / publishes the accumulators
+//   warps 0..3   epilogue    tcgen05.ld (32 lanes x 32 columns per warp), + bias, ReLU, 16-byte global stores
+// A CTA works on a SUPER-TILE of SM x SN output tiles of 128 x 128 (2x2, or 2x1 / 1x1 for narrow outputs) held in SM*SN
+// TMEM accumulators (128 lanes x 128 columns each): a 16-deep reduction block stages SM tiles of A and SN tiles of B once and
+// feeds SM*SN*6 MMAs, which halves the L2 -> SM operand traffic per flop against one tile per CTA (that traffic, not the
+// tensor pipe, bounded the one-tile version: measured).  With <= 2 accumulators per super-tile the TMEM allocation is
+// double-buffered so the epilogue overlaps the next super-tile.  Three 64 KB shared-memory stages.  Split-K (weight
+// gradients: the reduction runs over the env axis) writes partial tiles to a workspace; a second kernel sums them in a fixed
+// order, so results are bit-reproducible run to run.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/track2d.h"
 
@@ -33,16 +37,18 @@ void t2d_count_launches(int n);
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 32;
+constexpr int BM = 128, BN = 128, BK = 16;
 constexpr int STAGES = 3;
-constexpr int TILE_BYTES = BM * BK * 4;      // 16 KB; BM == BN
-constexpr int STAGE_BYTES = 4 * TILE_BYTES;  // A_hi | A_lo | B_hi | B_lo
+constexpr int TILE_BYTES = BM * BK * 4;      // 8 KB: one 128 x 16 fp32 operand tile (BM == BN)
+constexpr int SLOT_BYTES = 2 * TILE_BYTES;   // hi | lo
+constexpr int MAX_SLOTS = 4;                 // SM + SN <= 4 operand tiles per stage
+constexpr int STAGE_BYTES = MAX_SLOTS * SLOT_BYTES;  // 64 KB
 constexpr int EPI_WARPS = 4, MMA_WARP = 4, PROD_WARP0 = 5, PROD_WARPS = 16;
 constexpr int THREADS = (EPI_WARPS + 1 + PROD_WARPS) * 32;  // 672
-constexpr int PROD_THREADS = PROD_WARPS * 32;               // 512
-constexpr int NCH = BM * BK / 4 / PROD_THREADS;             // 16-byte chunks per producer thread per operand tile (2)
-constexpr int TMEM_COLS = 2 * BN;                           // two accumulator buffers
+constexpr int PROD_THREADS = PROD_WARPS * 32;               // 512 = the 16-byte chunks of one operand tile
+constexpr int TMEM_COLS = 512;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 128 /* barriers */;
+static_assert(BM * BK / 4 == PROD_THREADS, "one chunk per producer thread per operand tile");
 
 struct GemmParams {
     const float *A, *B;
@@ -50,7 +56,7 @@ struct GemmParams {
     const float *bias;  // [N] or null (applied here only when splits == 1)
     long long lda, ldb, ldd, split_stride;
     int M, N, K;
-    int tiles_m, tiles_n, splits, nkb;  // nkb = ceil(K / BK)
+    int st_m, st_n, splits, nkb;  // super-tile grid, split-K factor, nkb = ceil(K / BK)
     int relu;
 };
 
@@ -63,31 +69,23 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok = 0;
-    for (uint32_t spins = 0;; ++spins) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (ok) return;
-        if (spins > (1u << 24)) __trap();  // a lost arrival must not hang the device: fail the launch instead
-    }
+__device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
 }
-__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {  // long waits (epilogue): do not steal issue slots
-    uint32_t ok = 0;
-    for (uint32_t spins = 0;; ++spins) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (ok) return;
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    for (uint32_t spins = 0; !mbar_try(bar, parity); ++spins)
+        if (spins > (1u << 24)) __trap();  // a lost arrival must not hang the device: fail the launch instead
+}
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {  // long waits (epilogue): leave the issue slots alone
+    for (uint32_t spins = 0; !mbar_try(bar, parity); ++spins) {
         __nanosleep(100);
         if (spins > (1u << 22)) __trap();
     }
@@ -122,30 +120,32 @@ __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sy
 
 // UMMA shared-memory matrix descriptor.  Bits: [0,14) start address >> 4, [16,30) leading-dimension byte offset >> 4,
 // [32,46) stride-dimension byte offset >> 4, [46,48) descriptor version (1 on sm_100), [61,64) layout type
-// (2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B).
+// (4 = SWIZZLE_64B, 1 = SWIZZLE_128B_BASE32B).
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
            (1ull << 46) | ((uint64_t)layout_type << 61);
 }
-// Canonical layouts of one 128 (rows of M or N) x 32 (reduction) fp32 operand tile, 16 KB:
-//   K-major  (reduction index contiguous in global memory), SWIZZLE_128B: row r, 16-byte chunk c of its 128-byte line at
-//            (r/8)*1024 + (r%8)*128 + ((c ^ r%8) * 16);  LBO unused, SBO = 1024; the k-th 8-deep MMA starts 32*k bytes in
+// Canonical layouts of one 128 (rows of M or N) x 16 (reduction) fp32 operand tile, 8 KB.  Producer thread pt (0..511) owns
+// one 16-byte chunk of it:
+//   K-major  (reduction index contiguous in global memory), SWIZZLE_64B: row r = pt / 4, chunk c = pt % 4 of its 64-byte line
+//            at (r/8)*512 + (r%8)*64 + ((c ^ (r%8)/2) * 16);  LBO unused, SBO = 512 (next 8 rows); the k-th 8-deep MMA starts
+//            32*k bytes in
 //   MN-major (row index contiguous), SWIZZLE_128B_BASE32B -- the only MN-major layout the tensor core takes for 32-bit
 //            operands: atoms of 32 rows x 4 reduction indices (4 lines of 128 bytes) whose 32-byte chunks are XOR-ed with
-//            the line number.  Reduction index kk, 16-byte row chunk c32 (of 32) at
+//            the line number.  Reduction index kk = pt / 32, row chunk c32 = pt % 32 at
 //            (kk/4)*2048 + (c32/8)*512 + (kk%4)*128 + (((c32%8)/2 ^ kk%4) * 32) + (c32%2)*16;  LBO = 512 (next 32 rows),
 //            SBO = 2048 (next 4 reduction indices); the k-th 8-deep MMA starts 4096*k bytes in
 template <bool MN>
 __device__ __forceinline__ uint64_t tile_desc(uint32_t saddr, int k8) {
-    return MN ? umma_desc(saddr + 4096u * k8, 512u, 2048u, 1u) : umma_desc(saddr + 32u * k8, 16u, 1024u, 2u);
+    return MN ? umma_desc(saddr + 4096u * k8, 512u, 2048u, 1u) : umma_desc(saddr + 32u * k8, 16u, 512u, 4u);
 }
 template <bool MN>
-__device__ __forceinline__ uint32_t tile_offset(int pt, int i) {
+__device__ __forceinline__ uint32_t tile_offset(int pt) {
     if (!MN) {
-        const int row = (pt >> 3) + (PROD_THREADS / 8) * i, c = pt & 7;
-        return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((c ^ (row & 7)) << 4));
+        const int row = pt >> 2, c = pt & 3, r8 = row & 7;
+        return (uint32_t)((row >> 3) * 512 + r8 * 64 + ((c ^ (r8 >> 1)) << 4));
     } else {
-        const int kk = (pt >> 5) + (PROD_THREADS / 32) * i, c32 = pt & 31, kr = kk & 3, c = c32 & 7;
+        const int kk = pt >> 5, c32 = pt & 31, kr = kk & 3, c = c32 & 7;
         return (uint32_t)((kk >> 2) * 2048 + (c32 >> 3) * 512 + kr * 128 + ((((c >> 1) ^ kr) << 5) | ((c & 1) << 4)));
     }
 }
@@ -159,62 +159,75 @@ __device__ __forceinline__ void split1(float x, float &hi, float &lo) {
     lo = x - hi;
 }
 
-// One producer thread's view of an operand: the addresses of its NCH 16-byte chunks in the current reduction block, advanced
-// by a constant stride per block (no per-block index arithmetic)
-template <bool MN>
+// One producer thread's view of an operand: the address of its chunk in tile 0 of the current reduction block; tile j of the
+// super-tile is j * tile_step further; advanced by a constant stride per block (no per-block index arithmetic)
+template <bool MN, int NT>
 struct OperandCursor {
-    const float *ptr;     // chunk 0 of this thread in the current reduction block; chunk i is i * chunk_step further
-    long long chunk_step, block_step;
-    int kofs;             // reduction index of chunk 0 relative to the block start
-    uint32_t ok;          // bit i: chunk i lies inside the operand's M / N extent
-    __device__ __forceinline__ void set_tile(const float *X, long long ld, int mn0, int kb, int mn_lim, int pt) {
+    const float *ptr;
+    long long tile_step, block_step;
+    int kofs;     // reduction index of the chunk relative to the block start
+    uint32_t ok;  // bit j: the chunk of tile j lies inside the operand's M / N extent
+    __device__ __forceinline__ void set(const float *X, long long ld, int mn0, int kb, int mn_lim, int pt) {
         ok = 0;
+        int mn;
         if (!MN) {
-            const int mn = mn0 + (pt >> 3);
-            kofs = (pt & 7) * 4;
-            chunk_step = (long long)(PROD_THREADS / 8) * ld;
+            mn = mn0 + (pt >> 2);
+            kofs = (pt & 3) * 4;
+            tile_step = (long long)BM * ld;
             block_step = BK;
             ptr = X + (long long)mn * ld + (long long)kb * BK + kofs;
-#pragma unroll
-            for (int i = 0; i < NCH; ++i) ok |= (mn + (PROD_THREADS / 8) * i < mn_lim ? 1u : 0u) << i;
         } else {
-            const int mn = mn0 + (pt & 31) * 4;
+            mn = mn0 + (pt & 31) * 4;
             kofs = pt >> 5;
-            chunk_step = (long long)(PROD_THREADS / 32) * ld;
+            tile_step = BM;
             block_step = (long long)BK * ld;
             ptr = X + ((long long)kb * BK + kofs) * ld + mn;
-            ok = mn < mn_lim ? 0xFFFFFFFFu : 0u;
         }
-    }
-    __device__ __forceinline__ void load(float4 (&r)[NCH], int k0, int k_lim) {
 #pragma unroll
-        for (int i = 0; i < NCH; ++i) {
-            const int k = k0 + kofs + (MN ? (PROD_THREADS / 32) * i : 0);
-            r[i] = (((ok >> i) & 1u) && k < k_lim) ? __ldg(reinterpret_cast<const float4 *>(ptr + i * chunk_step)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        for (int j = 0; j < NT; ++j) ok |= (mn + BM * j < mn_lim ? 1u : 0u) << j;
+    }
+    __device__ __forceinline__ void load(float4 (&r)[NT], int k0, int k_lim) {
+        const bool k_ok = k0 + kofs < k_lim;
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+            r[j] = (((ok >> j) & 1u) && k_ok) ? __ldg(reinterpret_cast<const float4 *>(ptr + j * tile_step)) : make_float4(0.f, 0.f, 0.f, 0.f);
         ptr += block_step;
     }
 };
 
-template <bool MN>
-__device__ __forceinline__ void store_tile(uint32_t hi_base, uint32_t lo_base, const float4 (&r)[NCH], int pt) {
-#pragma unroll
-    for (int i = 0; i < NCH; ++i) {
-        float4 h, l;
-        split1(r[i].x, h.x, l.x);
-        split1(r[i].y, h.y, l.y);
-        split1(r[i].z, h.z, l.z);
-        split1(r[i].w, h.w, l.w);
-        const uint32_t off = tile_offset<MN>(pt, i);
-        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(hi_base + off), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
-        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(lo_base + off), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
-    }
+__device__ __forceinline__ void store_chunk(uint32_t hi_addr, const float4 &r) {
+    float4 h, l;
+    split1(r.x, h.x, l.x);
+    split1(r.y, h.y, l.y);
+    split1(r.z, h.z, l.z);
+    split1(r.w, h.w, l.w);
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(hi_addr), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(hi_addr + TILE_BYTES), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
 }
 
-template <bool A_MN, bool B_MN>
+struct Item {  // one unit of work of a CTA: a super-tile and a reduction range
+    int m0, n0, sp, kb0, kb1;
+};
+template <int SM, int SN>
+__device__ __forceinline__ Item decode_item(const GemmParams &p, int item) {
+    Item w;
+    const int tn = item % p.st_n, rest = item / p.st_n;
+    const int tm = rest % p.st_m;
+    w.sp = rest / p.st_m;
+    w.m0 = tm * SM * BM;
+    w.n0 = tn * SN * BN;
+    w.kb0 = (int)((long long)p.nkb * w.sp / p.splits);
+    w.kb1 = (int)((long long)p.nkb * (w.sp + 1) / p.splits);
+    return w;
+}
+
+template <bool A_MN, bool B_MN, int SM, int SN>
 __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const GemmParams p) {
+    constexpr int NACC = SM * SN;                             // accumulators (128 TMEM columns each) per super-tile
+    constexpr int NBUF = NACC * BN * 2 <= TMEM_COLS ? 2 : 1;  // double-buffer them when they fit
+    static_assert(SM + SN <= MAX_SLOTS && NACC * BN <= TMEM_COLS, "super-tile does not fit");
     extern __shared__ uint8_t smem_raw[];
-    const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
+    const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzle atoms need aligned tiles
     const uint32_t bars = smem0 + STAGES * STAGE_BYTES;
     // barriers: full[STAGES], empty[STAGES], acc_full[2], acc_empty[2]; then the TMEM base address
     const uint32_t bar_full = bars, bar_empty = bars + 8 * STAGES, bar_accf = bars + 16 * STAGES, bar_acce = bar_accf + 16;
@@ -222,7 +235,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const GemmParam
     uint32_t *tmem_slot_ptr = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_items = p.tiles_m * p.tiles_n * p.splits;
+    const int n_items = p.st_m * p.st_n * p.splits;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -247,19 +260,20 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const GemmParam
     if (warp >= PROD_WARP0) {
         // ===== producers =====
         const int pt = threadIdx.x - PROD_WARP0 * 32;
-        float4 a[3][NCH], b[3][NCH];
-        OperandCursor<A_MN> ca;
-        OperandCursor<B_MN> cb;
+        const uint32_t off_a = tile_offset<A_MN>(pt), off_b = tile_offset<B_MN>(pt);
+        float4 a[3][SM], b[3][SN];
+        OperandCursor<A_MN, SM> ca;
+        OperandCursor<B_MN, SN> cb;
         int item = blockIdx.x, kb = 0, kb_end = 0, n_loaded = 0;
-        auto set_item = [&]() {  // this CTA's next work item: (split, tile_m, tile_n) -> reduction-block range and operand cursors
+        auto set_item = [&]() {
             if (item >= n_items) return;
-            const int tn = item % p.tiles_n, tm = (item / p.tiles_n) % p.tiles_m, sp = item / (p.tiles_n * p.tiles_m);
-            kb = (int)((long long)p.nkb * sp / p.splits);
-            kb_end = (int)((long long)p.nkb * (sp + 1) / p.splits);
-            ca.set_tile(p.A, p.lda, tm * BM, kb, p.M, pt);
-            cb.set_tile(p.B, p.ldb, tn * BN, kb, p.N, pt);
+            const Item w = decode_item<SM, SN>(p, item);
+            kb = w.kb0;
+            kb_end = w.kb1;
+            ca.set(p.A, p.lda, w.m0, kb, p.M, pt);
+            cb.set(p.B, p.ldb, w.n0, kb, p.N, pt);
         };
-        auto issue = [&](float4 (&ra)[NCH], float4 (&rb)[NCH]) {
+        auto issue = [&](float4 (&ra)[SM], float4 (&rb)[SN]) {
             ca.load(ra, kb * BK, p.K);
             cb.load(rb, kb * BK, p.K);
             ++n_loaded;
@@ -280,8 +294,10 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const GemmParam
                     const int s = it % STAGES;
                     mbar_wait(bar_empty + 8 * s, ((it / STAGES) & 1) ^ 1);
                     const uint32_t st = smem0 + s * STAGE_BYTES;
-                    store_tile<A_MN>(st, st + TILE_BYTES, a[u], pt);
-                    store_tile<B_MN>(st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, b[u], pt);
+#pragma unroll
+                    for (int j = 0; j < SM; ++j) store_chunk(st + j * SLOT_BYTES + off_a, a[u][j]);
+#pragma unroll
+                    for (int j = 0; j < SN; ++j) store_chunk(st + (SM + j) * SLOT_BYTES + off_b, b[u][j]);
                     fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
                     mbar_arrive(bar_full + 8 * s);
                     ++it;
@@ -296,13 +312,13 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const GemmParam
                                ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
         int it = 0, t = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++t) {
-            const int sp = item / (p.tiles_n * p.tiles_m);
-            const int kb0 = (int)((long long)p.nkb * sp / p.splits), kb1 = (int)((long long)p.nkb * (sp + 1) / p.splits);
-            const int acc = t & 1;
-            mbar_wait(bar_acce + 8 * acc, ((t >> 1) & 1) ^ 1);  // epilogue has drained this accumulator buffer
+            const Item w = decode_item<SM, SN>(p, item);
+            const int buf = NBUF == 2 ? (t & 1) : 0;
+            const uint32_t use = NBUF == 2 ? (uint32_t)(t >> 1) : (uint32_t)t;  // how often this buffer has been used before
+            mbar_wait(bar_acce + 8 * buf, (use & 1) ^ 1);  // the epilogue has drained this accumulator buffer
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-            for (int kb = kb0; kb < kb1; ++kb, ++it) {
+            const uint32_t d_tmem = tmem_base + (uint32_t)(buf * NACC * BN);
+            for (int kb = w.kb0; kb < w.kb1; ++kb, ++it) {
                 const int s = it % STAGES;
                 mbar_wait(bar_full + 8 * s, (it / STAGES) & 1);
                 tc_fence_after();
@@ -310,56 +326,71 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const GemmParam
                     const uint32_t st = smem0 + s * STAGE_BYTES;
 #pragma unroll
                     for (int k8 = 0; k8 < BK / 8; ++k8) {
-                        const uint64_t a_hi = tile_desc<A_MN>(st, k8), a_lo = tile_desc<A_MN>(st + TILE_BYTES, k8);
-                        const uint64_t b_hi = tile_desc<B_MN>(st + 2 * TILE_BYTES, k8), b_lo = tile_desc<B_MN>(st + 3 * TILE_BYTES, k8);
-                        tc_mma_tf32(d_tmem, a_lo, b_hi, idesc, (kb > kb0 || k8 > 0) ? 1u : 0u);
-                        tc_mma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
-                        tc_mma_tf32(d_tmem, a_hi, b_hi, idesc, 1u);
+                        const uint32_t accum = (kb > w.kb0 || k8 > 0) ? 1u : 0u;
+#pragma unroll
+                        for (int i = 0; i < SM; ++i) {
+                            const uint64_t a_hi = tile_desc<A_MN>(st + i * SLOT_BYTES, k8), a_lo = tile_desc<A_MN>(st + i * SLOT_BYTES + TILE_BYTES, k8);
+#pragma unroll
+                            for (int j = 0; j < SN; ++j) {
+                                const uint64_t b_hi = tile_desc<B_MN>(st + (SM + j) * SLOT_BYTES, k8),
+                                               b_lo = tile_desc<B_MN>(st + (SM + j) * SLOT_BYTES + TILE_BYTES, k8);
+                                const uint32_t d = d_tmem + (uint32_t)((i * SN + j) * BN);
+                                tc_mma_tf32(d, a_lo, b_hi, idesc, accum);
+                                tc_mma_tf32(d, a_hi, b_lo, idesc, 1u);
+                                tc_mma_tf32(d, a_hi, b_hi, idesc, 1u);
+                            }
+                        }
                     }
-                    tc_commit(bar_empty + 8 * s);                     // stage free once these MMAs have read it
-                    if (kb == kb1 - 1) tc_commit(bar_accf + 8 * acc);  // accumulator complete
+                    tc_commit(bar_empty + 8 * s);                       // stage free once these MMAs have read it
+                    if (kb == w.kb1 - 1) tc_commit(bar_accf + 8 * buf);  // accumulators complete
                 }
                 __syncwarp();
             }
         }
     } else {
-        // ===== epilogue: warp w owns TMEM lanes [32w, 32w + 32) = tile rows =====
+        // ===== epilogue: warp w owns TMEM lanes [32w, 32w + 32) = rows of each tile =====
         int t = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++t) {
-            const int tn = item % p.tiles_n, tm = (item / p.tiles_n) % p.tiles_m, sp = item / (p.tiles_n * p.tiles_m);
-            const int acc = t & 1;
-            mbar_wait_backoff(bar_accf + 8 * acc, (t >> 1) & 1);
+            const Item w = decode_item<SM, SN>(p, item);
+            const int buf = NBUF == 2 ? (t & 1) : 0;
+            const uint32_t use = NBUF == 2 ? (uint32_t)(t >> 1) : (uint32_t)t;
+            mbar_wait_backoff(bar_accf + 8 * buf, use & 1);
             tc_fence_after();
-            const int row = tm * BM + warp * 32 + lane;
-            float *drow = p.D + (long long)sp * p.split_stride + (long long)row * p.ldd;
             const bool fused = p.splits == 1;
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                uint32_t r[32];
-                tc_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN + c * 32), r);
-                tc_wait_ld();
-                const int col0 = tn * BN + c * 32;
-                if (row < p.M) {
+            for (int ij = 0; ij < NACC; ++ij) {
+                const int i = ij / SN, j = ij % SN;
+                const int row = w.m0 + i * BM + warp * 32 + lane;
+                float *drow = p.D + (long long)w.sp * p.split_stride + (long long)row * p.ldd;
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    const int col0 = w.n0 + j * BN + c * 32;
+                    if (col0 >= p.N) break;  // warp-uniform
+                    uint32_t r[32];
+                    tc_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)((buf * NACC + ij) * BN + c * 32), r);
+                    tc_wait_ld();
+                    if (row < p.M) {
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const int col = col0 + 4 * q;
-                        if (col < p.N) {
-                            float4 v = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
-                                                   __uint_as_float(r[4 * q + 3]));
-                            if (fused) {
-                                if (p.bias) {
-                                    const float4 bv = __ldg(reinterpret_cast<const float4 *>(p.bias + col));
-                                    v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+                        for (int q = 0; q < 8; ++q) {
+                            const int col = col0 + 4 * q;
+                            if (col < p.N) {
+                                float4 v = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
+                                                       __uint_as_float(r[4 * q + 3]));
+                                if (fused) {
+                                    if (p.bias) {
+                                        const float4 bv = __ldg(reinterpret_cast<const float4 *>(p.bias + col));
+                                        v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+                                    }
+                                    if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
                                 }
-                                if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                                *reinterpret_cast<float4 *>(drow + col) = v;
                             }
-                            *reinterpret_cast<float4 *>(drow + col) = v;
                         }
                     }
                 }
             }
             tc_fence_before();
-            mbar_arrive(bar_acce + 8 * acc);
+            mbar_arrive(bar_acce + 8 * buf);
         }
     }
 
@@ -394,27 +425,50 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float *__restr
 
 int g_sm_count = 0;
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, int SM, int SN>
 cudaError_t launch(const GemmParams &p, int grid, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel<A_MN, B_MN, SM, SN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    gemm_tf32x3_kernel<A_MN, B_MN><<<grid, THREADS, SMEM_BYTES, st>>>(p);
+    gemm_tf32x3_kernel<A_MN, B_MN, SM, SN><<<grid, THREADS, SMEM_BYTES, st>>>(p);
     return cudaGetLastError();
+}
+
+template <int SM, int SN>
+cudaError_t launch_major(const GemmParams &p, int a_mn, int b_mn, int grid, cudaStream_t st) {
+    if (a_mn) return b_mn ? launch<true, true, SM, SN>(p, grid, st) : launch<true, false, SM, SN>(p, grid, st);
+    return b_mn ? launch<false, true, SM, SN>(p, grid, st) : launch<false, false, SM, SN>(p, grid, st);
+}
+
+// the launch plan is a pure function of the shape: super-tile (SM x SN tiles), super-tile grid, split-K factor
+struct Plan {
+    int sm, sn, st_m, st_n, splits, nkb;
+};
+Plan make_plan(int64_t M, int64_t N, int64_t K) {
+    Plan pl;
+    const int tiles_m = (int)((M + BM - 1) / BM), tiles_n = (int)((N + BN - 1) / BN);
+    pl.sm = tiles_m >= 2 ? 2 : 1;
+    pl.sn = tiles_n >= 2 ? 2 : 1;
+    if (pl.sm == 1 && pl.sn == 2) pl.sn = 1;  // (1,2) is not instantiated; one tile per CTA then
+    pl.st_m = (tiles_m + pl.sm - 1) / pl.sm;
+    pl.st_n = (tiles_n + pl.sn - 1) / pl.sn;
+    pl.nkb = (int)((K + BK - 1) / BK);
+    const int64_t items = (int64_t)pl.st_m * pl.st_n;
+    int64_t splits = items >= 96 ? 1 : (148 + items - 1) / items;  // fill the SMs when there are few super-tiles (weight gradients)
+    if (splits > pl.nkb) splits = pl.nkb;
+    pl.splits = (int)splits;
+    return pl;
 }
 
 }  // namespace
 
 extern "C" int64_t track2d_gemm_workspace_floats(int64_t M, int64_t N, int64_t K) {
-    // upper bound over the split counts track2d_gemm_tf32x3 may choose
-    const int64_t tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
-    const int64_t nkb = (K + BK - 1) / BK;
-    int64_t splits = tiles >= 96 ? 1 : (148 + tiles - 1) / tiles;
-    if (splits > nkb) splits = nkb;
-    return splits <= 1 ? 0 : splits * M * N;
+    if (M <= 0 || N <= 0 || K <= 0) return 0;
+    const Plan pl = make_plan(M, N, K);
+    return pl.splits <= 1 ? 0 : (int64_t)pl.splits * M * N;
 }
 
 extern "C" int track2d_gemm_tf32x3(const float *a_dev, int a_mn_major, int64_t lda, const float *b_dev, int b_mn_major, int64_t ldb,
@@ -439,29 +493,26 @@ extern "C" int track2d_gemm_tf32x3(const float *a_dev, int a_mn_major, int64_t l
             return T2D_E_CUDA;
         }
     }
+    const Plan pl = make_plan(M, N, K);
     GemmParams p;
     p.A = a_dev; p.B = b_dev; p.bias = bias_dev;
     p.lda = lda; p.ldb = ldb;
     p.M = (int)M; p.N = (int)N; p.K = (int)K;
-    p.tiles_m = (int)((M + BM - 1) / BM);
-    p.tiles_n = (int)((N + BN - 1) / BN);
-    p.nkb = (int)((K + BK - 1) / BK);
+    p.st_m = pl.st_m; p.st_n = pl.st_n; p.nkb = pl.nkb; p.splits = pl.splits;
     p.relu = relu;
-    const int64_t tiles = (int64_t)p.tiles_m * p.tiles_n;
-    int64_t splits = tiles >= 96 ? 1 : (148 + tiles - 1) / tiles;  // fill the SMs when there are few output tiles (weight gradients)
-    if (splits > p.nkb) splits = p.nkb;
+    const int64_t splits = pl.splits;
     if (splits > 1 && (!workspace_dev || workspace_floats < splits * M * N || (uintptr_t)workspace_dev % 16)) {
         t2d_set_error("track2d_gemm_tf32x3: split-K needs a workspace of %lld floats (track2d_gemm_workspace_floats)", (long long)(splits * M * N));
         return T2D_E_INVALID;
     }
-    p.splits = (int)splits;
     if (splits > 1) { p.D = workspace_dev; p.ldd = N; p.split_stride = M * N; }
     else { p.D = d_dev; p.ldd = ldd; p.split_stride = 0; }
-    const int64_t items = tiles * splits;
+    const int64_t items = (int64_t)pl.st_m * pl.st_n * splits;
     const int grid = (int)(items < g_sm_count ? items : g_sm_count);
     cudaError_t e;
-    if (a_mn_major) e = b_mn_major ? launch<true, true>(p, grid, st) : launch<true, false>(p, grid, st);
-    else e = b_mn_major ? launch<false, true>(p, grid, st) : launch<false, false>(p, grid, st);
+    if (pl.sm == 2 && pl.sn == 2) e = launch_major<2, 2>(p, a_mn_major, b_mn_major, grid, st);
+    else if (pl.sm == 2) e = launch_major<2, 1>(p, a_mn_major, b_mn_major, grid, st);
+    else e = launch_major<1, 1>(p, a_mn_major, b_mn_major, grid, st);
     if (e != cudaSuccess) {
         t2d_set_error("track2d_gemm_tf32x3: launch failed: %s", cudaGetErrorString(e));
         return T2D_E_CUDA;
