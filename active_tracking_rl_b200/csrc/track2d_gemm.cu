@@ -12,18 +12,18 @@
 // the result carries fp32 accuracy -- unlike plain TF32, which loses 13 mantissa bits of every input.
 //
 // Structure (one persistent CTA per SM, 21 warps, warp-specialised):
-//   warps 5..20  producers   coalesced 16-byte global loads (two reduction blocks prefetched in registers), hi/lo split,
-//                            st.shared into the UMMA canonical swizzled layouts (K-major or MN-major, so the same kernel
+//   warps 5..20  producers   cp.async 16-byte chunks into a 3-deep raw ring (two reduction blocks in flight), then each thread
+//                            re-reads its own chunks, splits them hi/lo and st.shared's them into the UMMA canonical swizzled layouts (K-major or MN-major, so the same kernel
 //                            runs y = x W^T, dx = dy W and dW = dy^T x without any transposed copy), fence.proxy.async +
 //                            mbarrier arrive
-//   warp 4       MMA issuer  one lane issues the tcgen05.mma's (128 x 128 x 8 each); tcgen05.commit releases the
+//   warp 4       MMA issuer  one lane issues the tcgen05.mma's (128 x 256 x 8 each for 2-wide super-tiles); tcgen05.commit releases the
 //                            shared-memory stage / publishes the accumulators
 //   warps 0..3   epilogue    tcgen05.ld (32 lanes x 32 columns per warp), + bias, ReLU, 16-byte global stores
 // A CTA works on a SUPER-TILE of SM x SN output tiles of 128 x 128 (2x2, or 2x1 / 1x1 for narrow outputs) held in SM*SN
 // TMEM accumulators (128 lanes x 128 columns each): a 16-deep reduction block stages SM tiles of A and SN tiles of B once and
-// feeds SM*SN*6 MMAs, which halves the L2 -> SM operand traffic per flop against one tile per CTA (that traffic, not the
+// feeds SM*6 MMAs of N = 128*SN, which halves the L2 -> SM operand traffic per flop against one tile per CTA (that traffic, not the
 // tensor pipe, bounded the one-tile version: measured).  With <= 2 accumulators per super-tile the TMEM allocation is
-// double-buffered so the epilogue overlaps the next super-tile.  Three 64 KB shared-memory stages.  Split-K (weight
+// double-buffered so the epilogue overlaps the next super-tile.  Two 64 KB operand stages + three 32 KB raw stages of shared memory.  Split-K (weight
 // gradients: the reduction runs over the env axis) writes partial tiles to a workspace; a second kernel sums them in a fixed
 // order, so results are bit-reproducible run to run.
 #include <cuda_runtime.h>
@@ -38,7 +38,8 @@ void t2d_count_launches(int n);
 namespace {
 
 constexpr int BM = 128, BN = 128, BK = 16;
-constexpr int STAGES = 3;
+constexpr int STAGES = 2;      // MMA operand stages (hi/lo tiles in the UMMA layouts)
+constexpr int RAW_STAGES = 3;  // cp.async landing ring of raw fp32 chunks (each thread re-reads only what it copied itself)
 constexpr int TILE_BYTES = BM * BK * 4;      // 8 KB: one 128 x 16 fp32 operand tile (BM == BN)
 constexpr int SLOT_BYTES = 2 * TILE_BYTES;   // hi | lo
 constexpr int MAX_SLOTS = 4;                 // SM + SN <= 4 operand tiles per stage
@@ -47,7 +48,8 @@ constexpr int EPI_WARPS = 4, MMA_WARP = 4, PROD_WARP0 = 5, PROD_WARPS = 16;
 constexpr int THREADS = (EPI_WARPS + 1 + PROD_WARPS) * 32;  // 672
 constexpr int PROD_THREADS = PROD_WARPS * 32;               // 512 = the 16-byte chunks of one operand tile
 constexpr int TMEM_COLS = 512;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 128 /* barriers */;
+constexpr int RAW_BYTES = MAX_SLOTS * TILE_BYTES;       // 32 KB
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + RAW_STAGES * RAW_BYTES + 1024 /* alignment slack */ + 128 /* barriers */;
 static_assert(BM * BK / 4 == PROD_THREADS, "one chunk per producer thread per operand tile");
 
 struct GemmParams {
@@ -93,6 +95,17 @@ __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// One elected lane issues the MMAs and the commits (a commit tracks the MMAs of the issuing thread).  elect.sync tells ptxas that
+// exactly one lane is active inside the branch, so the descriptors move to uniform registers without a per-value loop.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "elect.sync _|P, 0xFFFFFFFF;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -125,28 +138,33 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
            (1ull << 46) | ((uint64_t)layout_type << 61);
 }
-// Canonical layouts of one 128 (rows of M or N) x 16 (reduction) fp32 operand tile, 8 KB.  Producer thread pt (0..511) owns
-// one 16-byte chunk of it:
-//   K-major  (reduction index contiguous in global memory), SWIZZLE_64B: row r = pt / 4, chunk c = pt % 4 of its 64-byte line
-//            at (r/8)*512 + (r%8)*64 + ((c ^ (r%8)/2) * 16);  LBO unused, SBO = 512 (next 8 rows); the k-th 8-deep MMA starts
-//            32*k bytes in
+// Canonical layouts of a (128 * NT) (rows of M or N) x 16 (reduction) fp32 operand block, 8 KB per 128 rows.  NT = 1 for A (one
+// MMA covers 128 rows of M) and SN for B (one MMA covers up to 256 columns of N, i.e. two adjacent output tiles).  Producer
+// thread pt (0..511) owns one 16-byte chunk of every 128-row tile j:
+//   K-major  (reduction index contiguous in global memory), SWIZZLE_64B: row r = 128 j + pt / 4, chunk c = pt % 4 of its
+//            64-byte line at (r/8)*512 + (r%8)*64 + ((c ^ (r%8)/2) * 16);  LBO unused, SBO = 512 (next 8 rows); the k-th 8-deep
+//            MMA starts 32*k bytes in
 //   MN-major (row index contiguous), SWIZZLE_128B_BASE32B -- the only MN-major layout the tensor core takes for 32-bit
 //            operands: atoms of 32 rows x 4 reduction indices (4 lines of 128 bytes) whose 32-byte chunks are XOR-ed with
-//            the line number.  Reduction index kk = pt / 32, row chunk c32 = pt % 32 at
-//            (kk/4)*2048 + (c32/8)*512 + (kk%4)*128 + (((c32%8)/2 ^ kk%4) * 32) + (c32%2)*16;  LBO = 512 (next 32 rows),
-//            SBO = 2048 (next 4 reduction indices); the k-th 8-deep MMA starts 4096*k bytes in
-template <bool MN>
-__device__ __forceinline__ uint64_t tile_desc(uint32_t saddr, int k8) {
-    return MN ? umma_desc(saddr + 4096u * k8, 512u, 2048u, 1u) : umma_desc(saddr + 32u * k8, 16u, 512u, 4u);
+//            the line number.  Reduction index kk = pt / 32, row chunk c32 = pt % 32 of tile j at
+//            (kk/4)*2048*NT + j*2048 + (c32/8)*512 + (kk%4)*128 + (((c32%8)/2 ^ kk%4) * 32) + (c32%2)*16;  LBO = 512 (next 32
+//            rows), SBO = 2048*NT (next 4 reduction indices); the k-th 8-deep MMA starts 4096*NT*k bytes in
+template <bool MN, int NT>
+__device__ __forceinline__ uint64_t desc_base() {  // descriptor with a zero address field
+    return MN ? umma_desc(0u, 512u, 2048u * NT, 1u) : umma_desc(0u, 16u, 512u, 4u);
 }
-template <bool MN>
+template <bool MN, int NT>
+__device__ __forceinline__ constexpr uint32_t k8_step() { return MN ? 4096u * NT : 32u; }
+template <bool MN, int NT>
+__device__ __forceinline__ constexpr uint32_t tile_step_smem() { return MN ? 2048u : (uint32_t)TILE_BYTES; }
+template <bool MN, int NT>
 __device__ __forceinline__ uint32_t tile_offset(int pt) {
     if (!MN) {
         const int row = pt >> 2, c = pt & 3, r8 = row & 7;
         return (uint32_t)((row >> 3) * 512 + r8 * 64 + ((c ^ (r8 >> 1)) << 4));
     } else {
         const int kk = pt >> 5, c32 = pt & 31, kr = kk & 3, c = c32 & 7;
-        return (uint32_t)((kk >> 2) * 2048 + (c32 >> 3) * 512 + kr * 128 + ((((c >> 1) ^ kr) << 5) | ((c & 1) << 4)));
+        return (uint32_t)((kk >> 2) * 2048 * NT + (c32 >> 3) * 512 + kr * 128 + ((((c >> 1) ^ kr) << 5) | ((c & 1) << 4)));
     }
 }
 
@@ -186,23 +204,30 @@ struct OperandCursor {
 #pragma unroll
         for (int j = 0; j < NT; ++j) ok |= (mn + BM * j < mn_lim ? 1u : 0u) << j;
     }
-    __device__ __forceinline__ void load(float4 (&r)[NT], int k0, int k_lim) {
+    // cp.async (LDGSTS) this thread's chunk of every tile of the block into the raw ring; chunks outside the operand are
+    // zero-filled (src-size 0).  Completion is tracked per commit group, so several blocks stay in flight -- a register
+    // prefetch cannot do that: all the LDGs of a warp share one scoreboard and the first use waits for the newest one too.
+    __device__ __forceinline__ void issue(uint32_t raw_addr, int k0, int k_lim, const float *safe) {
         const bool k_ok = k0 + kofs < k_lim;
 #pragma unroll
-        for (int j = 0; j < NT; ++j)
-            r[j] = (((ok >> j) & 1u) && k_ok) ? __ldg(reinterpret_cast<const float4 *>(ptr + j * tile_step)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < NT; ++j) {
+            const bool in = ((ok >> j) & 1u) && k_ok;
+            const float *src = in ? ptr + j * tile_step : safe;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(raw_addr + j * TILE_BYTES), "l"(src), "r"(in ? 16 : 0) : "memory");
+        }
         ptr += block_step;
     }
 };
 
-__device__ __forceinline__ void store_chunk(uint32_t hi_addr, const float4 &r) {
-    float4 h, l;
+__device__ __forceinline__ void store_chunk(uint32_t hi_addr, uint32_t lo_delta, uint32_t raw_addr) {
+    float4 r, h, l;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(raw_addr) : "memory");
     split1(r.x, h.x, l.x);
     split1(r.y, h.y, l.y);
     split1(r.z, h.z, l.z);
     split1(r.w, h.w, l.w);
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(hi_addr), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(hi_addr + TILE_BYTES), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(hi_addr + lo_delta), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
 }
 
 struct Item {  // one unit of work of a CTA: a super-tile and a reduction range
@@ -260,11 +285,12 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const GemmParam
     if (warp >= PROD_WARP0) {
         // ===== producers =====
         const int pt = threadIdx.x - PROD_WARP0 * 32;
-        const uint32_t off_a = tile_offset<A_MN>(pt), off_b = tile_offset<B_MN>(pt);
-        float4 a[3][SM], b[3][SN];
+        // stage layout: A tile i at i * SLOT_BYTES (hi | lo); then the B block: SN tiles hi (one operand of 128 SN rows) | SN tiles lo
+        const uint32_t off_a = tile_offset<A_MN, 1>(pt), off_b = SM * SLOT_BYTES + tile_offset<B_MN, SN>(pt);
+        const uint32_t raw0 = smem0 + STAGES * STAGE_BYTES + pt * 16;  // this thread's chunk of slot 0, raw stage 0
         OperandCursor<A_MN, SM> ca;
         OperandCursor<B_MN, SN> cb;
-        int item = blockIdx.x, kb = 0, kb_end = 0, n_loaded = 0;
+        int item = blockIdx.x, kb = 0, kb_end = 0, n_issued = 0;
         auto set_item = [&]() {
             if (item >= n_items) return;
             const Item w = decode_item<SM, SN>(p, item);
@@ -273,43 +299,42 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const GemmParam
             ca.set(p.A, p.lda, w.m0, kb, p.M, pt);
             cb.set(p.B, p.ldb, w.n0, kb, p.N, pt);
         };
-        auto issue = [&](float4 (&ra)[SM], float4 (&rb)[SN]) {
-            ca.load(ra, kb * BK, p.K);
-            cb.load(rb, kb * BK, p.K);
-            ++n_loaded;
-            if (++kb == kb_end) {
-                item += gridDim.x;
-                set_item();
-            }
-        };
-        set_item();
-        if (item < n_items) issue(a[0], b[0]);
-        if (item < n_items) issue(a[1], b[1]);
-        int it = 0;
-        while (it < n_loaded) {
-#pragma unroll
-            for (int u = 0; u < 3; ++u) {
-                if (it < n_loaded) {
-                    if (item < n_items) issue(a[(u + 2) % 3], b[(u + 2) % 3]);  // two reduction blocks ahead
-                    const int s = it % STAGES;
-                    mbar_wait(bar_empty + 8 * s, ((it / STAGES) & 1) ^ 1);
-                    const uint32_t st = smem0 + s * STAGE_BYTES;
-#pragma unroll
-                    for (int j = 0; j < SM; ++j) store_chunk(st + j * SLOT_BYTES + off_a, a[u][j]);
-#pragma unroll
-                    for (int j = 0; j < SN; ++j) store_chunk(st + (SM + j) * SLOT_BYTES + off_b, b[u][j]);
-                    fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
-                    mbar_arrive(bar_full + 8 * s);
-                    ++it;
+        auto issue = [&]() {  // the next reduction block of this CTA's work sequence -> raw ring; always one commit group
+            if (item < n_items) {
+                const uint32_t raw = raw0 + (n_issued % RAW_STAGES) * RAW_BYTES;
+                ca.issue(raw, kb * BK, p.K, p.A);
+                cb.issue(raw + SM * TILE_BYTES, kb * BK, p.K, p.B);
+                ++n_issued;
+                if (++kb == kb_end) {
+                    item += gridDim.x;
+                    set_item();
                 }
             }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        set_item();
+#pragma unroll
+        for (int i = 0; i < RAW_STAGES - 1; ++i) issue();
+        for (int it = 0; it < n_issued; ++it) {
+            issue();                                                                    // RAW_STAGES - 1 blocks ahead
+            asm volatile("cp.async.wait_group %0;" ::"n"(RAW_STAGES - 1) : "memory");  // block `it` has landed
+            const int s = it % STAGES;
+            mbar_wait(bar_empty + 8 * s, ((it / STAGES) & 1) ^ 1);
+            const uint32_t st = smem0 + s * STAGE_BYTES, raw = raw0 + (it % RAW_STAGES) * RAW_BYTES;
+#pragma unroll
+            for (int j = 0; j < SM; ++j) store_chunk(st + j * SLOT_BYTES + off_a, TILE_BYTES, raw + j * TILE_BYTES);
+#pragma unroll
+            for (int j = 0; j < SN; ++j) store_chunk(st + off_b + j * tile_step_smem<B_MN, SN>(), SN * TILE_BYTES, raw + (SM + j) * TILE_BYTES);
+            fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
+            mbar_arrive(bar_full + 8 * s);
         }
     } else if (warp == MMA_WARP) {
         // ===== MMA issuer =====
         // instruction descriptor: D fp32 (bits 4-5 = 1), A and B TF32 (bits 7-9, 10-12 = 2), major-ness of A / B (bits 15, 16;
         // 1 = MN-major), N >> 3 (bits 17-22), M >> 4 (bits 24-28)
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
-                               ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+                               ((uint32_t)((SN * BN) >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        const uint64_t da = desc_base<A_MN, 1>(), db = desc_base<B_MN, SN>();
         int it = 0, t = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++t) {
             const Item w = decode_item<SM, SN>(p, item);
@@ -322,23 +347,21 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const GemmParam
                 const int s = it % STAGES;
                 mbar_wait(bar_full + 8 * s, (it / STAGES) & 1);
                 tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t st = smem0 + s * STAGE_BYTES;
+                const uint32_t st16 = (smem0 + s * STAGE_BYTES) >> 4;  // the descriptors' address field counts 16-byte units
+                if (elect_one()) {
 #pragma unroll
                     for (int k8 = 0; k8 < BK / 8; ++k8) {
                         const uint32_t accum = (kb > w.kb0 || k8 > 0) ? 1u : 0u;
+                        const uint64_t b_hi = db + (st16 + ((SM * SLOT_BYTES + k8 * k8_step<B_MN, SN>()) >> 4));
+                        const uint64_t b_lo = b_hi + ((SN * TILE_BYTES) >> 4);
 #pragma unroll
-                        for (int i = 0; i < SM; ++i) {
-                            const uint64_t a_hi = tile_desc<A_MN>(st + i * SLOT_BYTES, k8), a_lo = tile_desc<A_MN>(st + i * SLOT_BYTES + TILE_BYTES, k8);
-#pragma unroll
-                            for (int j = 0; j < SN; ++j) {
-                                const uint64_t b_hi = tile_desc<B_MN>(st + (SM + j) * SLOT_BYTES, k8),
-                                               b_lo = tile_desc<B_MN>(st + (SM + j) * SLOT_BYTES + TILE_BYTES, k8);
-                                const uint32_t d = d_tmem + (uint32_t)((i * SN + j) * BN);
-                                tc_mma_tf32(d, a_lo, b_hi, idesc, accum);
-                                tc_mma_tf32(d, a_hi, b_lo, idesc, 1u);
-                                tc_mma_tf32(d, a_hi, b_hi, idesc, 1u);
-                            }
+                        for (int i = 0; i < SM; ++i) {  // one MMA covers the SN adjacent accumulators of tile row i (N = 128 SN)
+                            const uint64_t a_hi = da + (st16 + ((i * SLOT_BYTES + k8 * k8_step<A_MN, 1>()) >> 4));
+                            const uint64_t a_lo = a_hi + (TILE_BYTES >> 4);
+                            const uint32_t d = d_tmem + (uint32_t)(i * SN * BN);
+                            tc_mma_tf32(d, a_lo, b_hi, idesc, accum);
+                            tc_mma_tf32(d, a_hi, b_lo, idesc, 1u);
+                            tc_mma_tf32(d, a_hi, b_hi, idesc, 1u);
                         }
                     }
                     tc_commit(bar_empty + 8 * s);                       // stage free once these MMAs have read it
