@@ -25,6 +25,14 @@ void t2d_count_launches(int n);
 
 namespace {
 
+// Blackwell's packed fp32 FMA (fma.rn.f32x2 -> FFMA2): two independent round-to-nearest FMAs per instruction, i.e. the same
+// arithmetic as two fmaf() at half the issue slots (a scalar FFMA occupies the FMA pipe for 2 cycles per warp either way).
+__device__ __forceinline__ void ffma2(float2 &acc, const float2 a, const float2 b) {
+    unsigned long long c = *reinterpret_cast<unsigned long long *>(&acc);
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(*reinterpret_cast<const unsigned long long *>(&a)), "l"(*reinterpret_cast<const unsigned long long *>(&b)));
+    acc = *reinterpret_cast<float2 *>(&c);
+}
+
 constexpr int IMG = 8;          // images per CTA iteration
 constexpr int THREADS = 128;
 constexpr int XP = 15 * 15;     // zero-bordered input
@@ -104,9 +112,9 @@ __global__ void __launch_bounds__(THREADS) maze_conv_fwd_kernel(const float *__r
     for (int64_t n0 = (int64_t)blockIdx.x * IMG; n0 < N; n0 += (int64_t)gridDim.x * IMG) {
         const int nimg = (int)min((int64_t)IMG, N - n0);
         stage_and_conv1(s, x, n0, nimg, tid);
-        float accA[16], accB[16];
+        float2 accA[8], accB[8];  // output-channel pairs
 #pragma unroll
-        for (int c = 0; c < 16; c++) accA[c] = accB[c] = s.b2[och * 16 + c];
+        for (int c = 0; c < 8; c++) accA[c] = accB[c] = make_float2(s.b2[och * 16 + 2 * c], s.b2[och * 16 + 2 * c + 1]);
         const float *yi = &s.y1[img][0][(2 * oi) * 9 + 2 * oj0];
 #pragma unroll 2
         for (int ic = 0; ic < 16; ic++) {
@@ -118,25 +126,24 @@ __global__ void __launch_bounds__(THREADS) maze_conv_fwd_kernel(const float *__r
 #pragma unroll
             for (int k = 0; k < 9; k++) {
                 const float4 *wr = reinterpret_cast<const float4 *>(&s.w2t[(ic * 9 + k) * 32 + och * 16]);
-                const float va = v[k / 3][k % 3], vb = v[k / 3][k % 3 + 2];
+                const float2 va = make_float2(v[k / 3][k % 3], v[k / 3][k % 3]), vb = make_float2(v[k / 3][k % 3 + 2], v[k / 3][k % 3 + 2]);
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
                     const float4 wv = wr[q];
-                    accA[4 * q + 0] = fmaf(va, wv.x, accA[4 * q + 0]);
-                    accA[4 * q + 1] = fmaf(va, wv.y, accA[4 * q + 1]);
-                    accA[4 * q + 2] = fmaf(va, wv.z, accA[4 * q + 2]);
-                    accA[4 * q + 3] = fmaf(va, wv.w, accA[4 * q + 3]);
-                    accB[4 * q + 0] = fmaf(vb, wv.x, accB[4 * q + 0]);
-                    accB[4 * q + 1] = fmaf(vb, wv.y, accB[4 * q + 1]);
-                    accB[4 * q + 2] = fmaf(vb, wv.z, accB[4 * q + 2]);
-                    accB[4 * q + 3] = fmaf(vb, wv.w, accB[4 * q + 3]);
+                    ffma2(accA[2 * q + 0], va, make_float2(wv.x, wv.y));
+                    ffma2(accA[2 * q + 1], va, make_float2(wv.z, wv.w));
+                    ffma2(accB[2 * q + 0], vb, make_float2(wv.x, wv.y));
+                    ffma2(accB[2 * q + 1], vb, make_float2(wv.z, wv.w));
                 }
             }
         }
         if (img < nimg) {
             float *o = y2 + (n0 + img) * 512 + (och * 16) * 16 + oi * 4 + oj0;
 #pragma unroll
-            for (int c = 0; c < 16; c++) *reinterpret_cast<float2 *>(o + c * 16) = make_float2(fmaxf(accA[c], 0.f), fmaxf(accB[c], 0.f));
+            for (int c = 0; c < 8; c++) {
+                *reinterpret_cast<float2 *>(o + (2 * c) * 16) = make_float2(fmaxf(accA[c].x, 0.f), fmaxf(accB[c].x, 0.f));
+                *reinterpret_cast<float2 *>(o + (2 * c + 1) * 16) = make_float2(fmaxf(accA[c].y, 0.f), fmaxf(accB[c].y, 0.f));
+            }
         }
         __syncthreads(); // y1 / xs are rewritten by the next iteration
     }
@@ -156,11 +163,9 @@ __global__ void __launch_bounds__(THREADS) maze_conv_bwd_kernel(const float *__r
 
     // persistent accumulators
     const int ocg = tid & 7, icw = tid >> 3;    // dW2 tile: output channels 4*ocg..4*ocg+3, input channel icw
-    float aw2[4][9];
+    float2 aw2[9][2];  // [tap][output-channel pair]
 #pragma unroll
-    for (int a = 0; a < 4; a++)
-#pragma unroll
-        for (int k = 0; k < 9; k++) aw2[a][k] = 0.f;
+    for (int k = 0; k < 9; k++) aw2[k][0] = aw2[k][1] = make_float2(0.f, 0.f);
     const int img = tid >> 4, ic = tid & 15;    // dy1 / dW1 tile: (image, conv1 channel)
     float aw1[9], ab1 = 0.f, ab2 = 0.f;
 #pragma unroll
@@ -202,11 +207,11 @@ __global__ void __launch_bounds__(THREADS) maze_conv_bwd_kernel(const float *__r
                     for (int cj = 0; cj < 5; cj++) v[ki][cj] = yi[(2 * oi + ki) * 9 + 2 * oj0 + cj];
 #pragma unroll
                 for (int k = 0; k < 9; k++) {
-                    const float va = v[k / 3][k % 3], vb = v[k / 3][k % 3 + 2];
-                    aw2[0][k] = fmaf(dB.x, vb, fmaf(dA.x, va, aw2[0][k]));
-                    aw2[1][k] = fmaf(dB.y, vb, fmaf(dA.y, va, aw2[1][k]));
-                    aw2[2][k] = fmaf(dB.z, vb, fmaf(dA.z, va, aw2[2][k]));
-                    aw2[3][k] = fmaf(dB.w, vb, fmaf(dA.w, va, aw2[3][k]));
+                    const float2 va = make_float2(v[k / 3][k % 3], v[k / 3][k % 3]), vb = make_float2(v[k / 3][k % 3 + 2], v[k / 3][k % 3 + 2]);
+                    ffma2(aw2[k][0], make_float2(dA.x, dA.y), va);
+                    ffma2(aw2[k][1], make_float2(dA.z, dA.w), va);
+                    ffma2(aw2[k][0], make_float2(dB.x, dB.y), vb);
+                    ffma2(aw2[k][1], make_float2(dB.z, dB.w), vb);
                 }
             }
         }
@@ -217,9 +222,11 @@ __global__ void __launch_bounds__(THREADS) maze_conv_bwd_kernel(const float *__r
         }
 
         // ---- dy1[img][ic][7x7] = sum_{oc,pos,k} dz2[img][pos][oc] * w2[oc][ic][k]; then dz1 = dy1 * (y1 > 0) ------
-        float dy[49];
+        float2 dy[7][4];  // rows of 7 as column pairs (0,1) (2,3) (4,5) (6,-): taps kj = 1, 2 of an output position hit one pair
 #pragma unroll
-        for (int p = 0; p < 49; p++) dy[p] = 0.f;
+        for (int r = 0; r < 7; r++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) dy[r][c] = make_float2(0.f, 0.f);
         for (int oc = 0; oc < 32; oc++) {
             float w[9];
 #pragma unroll
@@ -227,13 +234,15 @@ __global__ void __launch_bounds__(THREADS) maze_conv_bwd_kernel(const float *__r
 #pragma unroll
             for (int pos = 0; pos < 16; pos++) {
                 const float d = s.dz2[img][pos][oc];
+                const float2 dd = make_float2(d, d);
 #pragma unroll
-                for (int ki = 0; ki < 3; ki++)
-#pragma unroll
-                    for (int kj = 0; kj < 3; kj++) {
-                        const int r = 2 * (pos >> 2) + ki - 1, c = 2 * (pos & 3) + kj - 1; // compile-time after unrolling
-                        if (r >= 0 && r < 7 && c >= 0 && c < 7) dy[r * 7 + c] = fmaf(d, w[ki * 3 + kj], dy[r * 7 + c]);
+                for (int ki = 0; ki < 3; ki++) {
+                    const int r = 2 * (pos >> 2) + ki - 1, px = pos & 3;  // compile-time after unrolling
+                    if (r >= 0 && r < 7) {
+                        ffma2(dy[r][px], dd, make_float2(w[ki * 3 + 1], w[ki * 3 + 2]));               // columns 2px, 2px + 1
+                        if (px > 0) dy[r][px - 1].y = fmaf(d, w[ki * 3], dy[r][px - 1].y);              // column 2px - 1
                     }
+                }
             }
         }
         // ---- dW1[ch][k] += sum dz1 * xpad ; db1 ----------------------------------------------------------------
@@ -244,7 +253,7 @@ __global__ void __launch_bounds__(THREADS) maze_conv_bwd_kernel(const float *__r
             for (int i = 0; i < 7; i++)
 #pragma unroll
                 for (int j = 0; j < 7; j++) {
-                    const float dz = yi[(i + 1) * 9 + j + 1] > 0.f ? dy[i * 7 + j] : 0.f;
+                    const float dz = yi[(i + 1) * 9 + j + 1] > 0.f ? ((j & 1) ? dy[i][j >> 1].y : dy[i][j >> 1].x) : 0.f;
                     ab1 += dz;
 #pragma unroll
                     for (int ki = 0; ki < 3; ki++)
@@ -259,7 +268,7 @@ __global__ void __launch_bounds__(THREADS) maze_conv_bwd_kernel(const float *__r
 #pragma unroll
     for (int a = 0; a < 4; a++)
 #pragma unroll
-        for (int k = 0; k < 9; k++) atomicAdd(&dw2[(ocg * 4 + a) * 144 + icw * 9 + k], aw2[a][k]);
+        for (int k = 0; k < 9; k++) atomicAdd(&dw2[(ocg * 4 + a) * 144 + icw * 9 + k], (a & 1) ? aw2[k][a >> 1].y : aw2[k][a >> 1].x);
     if (tid < 32) atomicAdd(&db2[tid], ab2);
     // dW1 / db1: 8 threads (one per image slot) share a channel: reduce through shared memory first
     float *red = reinterpret_cast<float *>(&s.dz2[0][0][0]);
