@@ -89,3 +89,56 @@ def linear(x, weight, bias=None, relu=False):
         return _Linear.apply(x, weight, bias, relu)
     y = torch.nn.functional.linear(x, weight, bias)
     return torch.relu(y) if relu else y
+
+
+class _LSTMCellPointwise(torch.autograd.Function):
+    """hy, cy = lstm_pointwise(igates, hgates, cx, b_ih, b_hh) -- csrc/track2d_lstm.cu.  The backward also produces the bias
+    gradient (column sums of dgates) in the same pass, in a fixed summation order."""
+
+    @staticmethod
+    def forward(ctx, igates, hgates, cx, b_ih, b_hh):
+        lib = _lib.load()
+        E, H4 = igates.shape
+        H = H4 // 4
+        dev = igates.device
+        hy = torch.empty((E, H), dtype=torch.float32, device=dev)
+        cy = torch.empty((E, H), dtype=torch.float32, device=dev)
+        act = torch.empty((E, H4), dtype=torch.float32, device=dev)
+        _lib.check(lib.track2d_lstm_cell_forward(_p(igates), _p(hgates), _p(b_ih), _p(b_hh), _p(cx), cx.stride(0), _p(hy), _p(cy), _p(act), E, H,
+                                                 C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), lib)
+        ctx.save_for_backward(cx, cy, act)
+        ctx.set_materialize_grads(False)
+        return hy, cy
+
+    @staticmethod
+    def backward(ctx, dhy, dcy):
+        lib = _lib.load()
+        cx, cy, act = ctx.saved_tensors
+        E, H4 = act.shape
+        H = H4 // 4
+        dev = act.device
+        if dhy is not None and (dhy.stride(1) != 1 or dhy.stride(0) % 4 or dhy.data_ptr() % 16):
+            dhy = dhy.contiguous()
+        if dcy is not None and (dcy.stride(1) != 1 or dcy.stride(0) % 4 or dcy.data_ptr() % 16):
+            dcy = dcy.contiguous()
+        dgates = torch.empty((E, H4), dtype=torch.float32, device=dev)
+        dcx = torch.empty((E, H), dtype=torch.float32, device=dev)
+        db = torch.empty(H4, dtype=torch.float32, device=dev)
+        n_ws = int(lib.track2d_lstm_bias_workspace_floats(E, H))
+        key = (dev.index, "lstm", n_ws)
+        ws = _WS.get(key)
+        if ws is None:
+            ws = _WS[key] = torch.empty(n_ws, dtype=torch.float32, device=dev)
+        _lib.check(lib.track2d_lstm_cell_backward(_p(dhy), dhy.stride(0) if dhy is not None else H, _p(dcy), dcy.stride(0) if dcy is not None else H,
+                                                  _p(cx), cx.stride(0), _p(cy), _p(act), _p(dgates), _p(dcx), _p(db), _p(ws), n_ws, E, H,
+                                                  C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), lib)
+        return dgates, dgates, dcx, db, db
+
+
+def lstm_pointwise_supported(igates, cx):
+    return (igates.is_cuda and igates.dtype == torch.float32 and igates.shape[1] == 512 and igates.is_contiguous() and cx.stride(1) == 1
+            and cx.stride(0) % 4 == 0 and cx.data_ptr() % 16 == 0)
+
+
+def lstm_pointwise(igates, hgates, cx, b_ih, b_hh):
+    return _LSTMCellPointwise.apply(igates, hgates, cx, b_ih, b_hh)

@@ -116,6 +116,8 @@ def _lstm_cell(lstm, x, hx, cx):
         from . import gemm
         igates = gemm.linear(x, lstm.weight_ih)
         hgates = gemm.linear(hx, lstm.weight_hh)
+        if gemm.lstm_pointwise_supported(igates, cx):
+            return gemm.lstm_pointwise(igates, hgates, cx, lstm.bias_ih, lstm.bias_hh)
         hy, cy, _ = torch.ops.aten._thnn_fused_lstm_cell(igates, hgates, cx, lstm.bias_ih, lstm.bias_hh)
         return hy, cy
     return lstm(x, (hx, cx))

@@ -332,7 +332,9 @@ def run_gpu_arm(a):
         "config": {"workload": "%s, %d envs per GPU, tat-maze-lstm tracker+target + aux reward (full AD-VAT), rollout %d steps + 1 update per step"
                                % (ENV_ID, E, T), "envs_per_gpu": E, "rollout_steps": T, "parallelism": "dp%d" % world,
                    "rng": "philox", "l2": "rollout observation buffers (21 x %.0f MB) and the roofline ring exceed the 126 MB L2" % (obs_b / 1e6),
-                   "policy_math": "float32 (TF32 off)" + ("; GEMMs via " + emu["reason"] if emu and emu["enabled"] else "; cuBLAS SIMT SGEMM"),
+                   "policy_math": "float32; fc / LSTM GEMMs (forward, dgrad, wgrad) on tcgen05 with the 3xTF32 split (track2d_gemm_tf32x3, "
+                                  "fp32-accurate: |err| <= 2e-6 |A||B|, tests/test_gpu_gemm.py); conv stack fp32 FFMA2; heads cuBLAS SIMT"
+                                  + ("; remaining cuBLAS GEMMs via " + emu["reason"] if emu and emu["enabled"] else ""),
                    "max_grad_norm": args.max_grad_norm, "launch_mode": mode},
         "roofline": roofline, "env_only": env_only, "cpu_baseline": cpu_base, "e2e": e2e, "clocks": clocks,
         "gpu_launches": int(launches), "device_status": status, "replicas_identical": replicas_identical,

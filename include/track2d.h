@@ -209,6 +209,20 @@ int track2d_gemm_tf32x3(const float *a_dev, int a_mn_major, int64_t lda, const f
                         float *d_dev, int64_t ldd, int64_t M, int64_t N, int64_t K, const float *bias_dev, int relu,
                         float *workspace_dev, int64_t workspace_floats, void *stream);
 
+/* The pointwise half of nn.LSTMCell (model.py:116,176) for E rows, hidden size H (128): gates = igates + hgates + b_ih + b_hh
+ * in PyTorch's [i | f | g | o] order -> hy, cy [E][H] and the activated gates act [E][4H] (kept for the backward).  cx may be a
+ * strided view (row stride cx_stride floats).  The backward takes dL/dhy, dL/dcy (either may be NULL = zero; row strides in
+ * floats) and writes dgates [E][4H] (the gradient of igates AND of hgates), dcx [E][H] and dbias [4H] (the gradient of b_ih and
+ * of b_hh: the column sums of dgates, combined in a fixed order through a workspace of
+ * track2d_lstm_bias_workspace_floats(E, H) floats).  Device pointers, 16-byte aligned. */
+int64_t track2d_lstm_bias_workspace_floats(int64_t E, int32_t H);
+int track2d_lstm_cell_forward(const float *igates_dev, const float *hgates_dev, const float *b_ih_dev, const float *b_hh_dev,
+                              const float *cx_dev, int64_t cx_stride, float *hy_dev, float *cy_dev, float *act_dev, int64_t E, int32_t H,
+                              void *stream);
+int track2d_lstm_cell_backward(const float *dhy_dev, int64_t dhy_stride, const float *dcy_dev, int64_t dcy_stride, const float *cx_dev,
+                               int64_t cx_stride, const float *cy_dev, const float *act_dev, float *dgates_dev, float *dcx_dev,
+                               float *dbias_dev, float *workspace_dev, int64_t workspace_floats, int64_t E, int32_t H, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

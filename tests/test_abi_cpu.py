@@ -66,6 +66,23 @@ def test_create_rejects_bad_config_without_touching_a_gpu():
     assert b"obs_type" in lib.track2d_last_error()
 
 
+def test_gemm_plan_and_argument_checks_without_a_gpu():
+    lib = _lib.load()
+    # the launch plan is a pure function of the shape: many super-tiles -> no split-K workspace; weight gradients
+    # (few output tiles, reduction over the env axis) -> split-K partials of M * N floats each
+    assert lib.track2d_gemm_workspace_floats(65536, 256, 1024) == 0
+    ws = lib.track2d_gemm_workspace_floats(256, 1024, 65536)
+    assert ws > 0 and ws % (256 * 1024) == 0 and ws // (256 * 1024) <= 148
+    assert lib.track2d_gemm_workspace_floats(0, 256, 16) == 0
+    null = ctypes.c_void_p(0)
+    assert lib.track2d_gemm_tf32x3(null, 0, 16, null, 0, 16, null, 16, 16, 16, 16, null, 0, null, 0, null) == -1
+    assert b"track2d_gemm_tf32x3" in lib.track2d_last_error()
+    # extents that are not multiples of 4 are refused before any launch (pointers are never dereferenced on the host)
+    fake = ctypes.c_void_p(4096)
+    assert lib.track2d_gemm_tf32x3(fake, 0, 8, fake, 0, 8, fake, 8, 8, 8, 6, null, 0, null, 0, null) == -1
+    assert b"multiples of 4" in lib.track2d_last_error()
+
+
 def test_product_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "active_tracking_rl_b200")
     for dirpath, _, files in os.walk(pkg):

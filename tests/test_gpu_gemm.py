@@ -68,3 +68,36 @@ def test_rejects_unaligned():
     b = torch.randn(8, 6, device="cuda:0")
     with pytest.raises(_lib.Track2DError):
         G.gemm(a, 0, 6, b, 0, 6, 8, 8, 6)
+
+
+def test_lstm_pointwise_matches_torch_lstmcell():
+    """csrc/track2d_lstm.cu against nn.LSTMCell's own fused pointwise op (forward values, all five gradients), with the strided
+    cx / dhy / dcy views the batched A3C_Dueling produces (hx, cx are slices of (E, 2, 128) tensors)."""
+    from active_tracking_rl_b200 import gemm as G
+    dev = "cuda:0"
+    g = torch.Generator(device=dev).manual_seed(11)
+    E, H = 1000, 128
+    ig = torch.randn(E, 4 * H, generator=g, device=dev, requires_grad=True)
+    hg = torch.randn(E, 4 * H, generator=g, device=dev, requires_grad=True)
+    cx2 = torch.randn(E, 2, H, generator=g, device=dev, requires_grad=True)
+    b_ih = torch.randn(4 * H, generator=g, device=dev, requires_grad=True)
+    b_hh = torch.randn(4 * H, generator=g, device=dev, requires_grad=True)
+    gh = torch.randn(E, 2, H, generator=g, device=dev)
+    gc = torch.randn(E, 2, H, generator=g, device=dev)
+    cx = cx2[:, 1]
+    assert G.lstm_pointwise_supported(ig, cx)
+    hy, cy = G.lstm_pointwise(ig, hg, cx, b_ih, b_hh)
+    hy_r, cy_r, _ = torch.ops.aten._thnn_fused_lstm_cell(ig, hg, cx, b_ih, b_hh)
+    assert torch.allclose(hy, hy_r, rtol=1e-5, atol=1e-6) and torch.allclose(cy, cy_r, rtol=1e-5, atol=1e-6)
+    ins = (ig, hg, cx2, b_ih, b_hh)
+    got = torch.autograd.grad((hy, cy), ins, (gh[:, 0], gc[:, 1]))
+    ref = torch.autograd.grad((hy_r, cy_r), ins, (gh[:, 0], gc[:, 1]))
+    for a, b in zip(got, ref):
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-5 * float(b.abs().max()) + 1e-6)
+    # only hy used downstream (dcy = None inside the Function), and bit-reproducible bias gradients
+    got2 = torch.autograd.grad(G.lstm_pointwise(ig, hg, cx, b_ih, b_hh)[0], ins, gh[:, 0])
+    ref2 = torch.autograd.grad(torch.ops.aten._thnn_fused_lstm_cell(ig, hg, cx, b_ih, b_hh)[0], ins, gh[:, 0])
+    for a, b in zip(got2, ref2):
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-5 * float(b.abs().max()) + 1e-6)
+    got3 = torch.autograd.grad(G.lstm_pointwise(ig, hg, cx, b_ih, b_hh)[0], ins, gh[:, 0])
+    assert torch.equal(got2[3], got3[3])
