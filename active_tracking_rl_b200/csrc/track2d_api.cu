@@ -227,7 +227,7 @@ int track2d_create(const track2d_config *cfg, track2d_env **out) {
     if (nav) {
         ALLOC(w.nav_plan, (size_t)E * T2D_NAV_PLAN_BYTES);
         w.astar_slots = t2d_nav_slots();
-        ALLOC(w.astar_ws, (size_t)w.astar_slots * (82 * 82) * 12);
+        ALLOC(w.astar_ws, (size_t)w.astar_slots * (82 * 82) * 16);  // HeapEntry spill area per concurrent plan
     }
     if (cfg->rng_mode == T2D_RNG_NUMPY) {
         ALLOC(w.mt_key, (size_t)E * T2D_MT_N);
