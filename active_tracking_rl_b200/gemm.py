@@ -24,8 +24,13 @@ def _p(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
+_WS_FLOATS = {}
+
+
 def _workspace(lib, M, N, K, device):
-    n = int(lib.track2d_gemm_workspace_floats(M, N, K))
+    n = _WS_FLOATS.get((M, N, K))
+    if n is None:  # the launch plan is a pure function of the shape: ask the library once
+        n = _WS_FLOATS[(M, N, K)] = int(lib.track2d_gemm_workspace_floats(M, N, K))
     if n == 0:
         return None, 0
     key = (device.index, n)

@@ -159,7 +159,7 @@ class Agent(object):
         return self.ret_buf[:T], self.gae_buf[:T]
 
     def optimize(self, params, optimizer, shared_model, training_mode, device_share=None, world_size=1, allreduce=None,
-                 boot_forced_actions=None):
+                 boot_forced_actions=None, apply=True):
         """Agent.optimize (player_util.py:108-161): bootstrap, n-step return + GAE, A3C losses of both agents,
         aux reward-prediction L1, backward, (all-reduce), [clip] + SharedAdam.  `params`, `shared_model` and
         `device_share` are accepted for call compatibility: the model IS the shared model here."""
@@ -199,7 +199,16 @@ class Agent(object):
             loss = loss + pred_loss
         optimizer.zero_grad()
         loss.mean().backward()  # mean over envs == average of the per-worker gradients
-        if allreduce is not None and world_size > 1:
+        self._stats = (policy_loss.detach(), value_loss.detach(), entropies.detach().sum(0), pred_loss.detach())
+        if apply:
+            self.apply_update(optimizer, world_size, allreduce)
+        return self._stats
+
+    def apply_update(self, optimizer, world_size=1, allreduce=None, skip_allreduce=False):
+        """second half of optimize(): [all-reduce of the flat gradient], [clip] + SharedAdam, and the hand-over of observation /
+        recurrent state to the next rollout.  Split off so that a multi-GPU run can replay the two halves as CUDA graphs with the
+        NCCL all-reduce launched eagerly between them."""
+        if allreduce is not None and world_size > 1 and not skip_allreduce:
             allreduce(optimizer.fp.grad)
         optimizer.step(max_grad_norm=self.max_grad_norm, grad_scale=1.0 / world_size)
         self.clear_actions()
@@ -208,4 +217,4 @@ class Agent(object):
         self.hx_store.copy_(self.hxs.detach())  # the next rollout starts from the stored state (fixed addresses)
         self.cx_store.copy_(self.cxs.detach())
         self.hxs, self.cxs = self.hx_store, self.cx_store
-        return policy_loss.detach(), value_loss.detach(), entropies.detach().sum(0), pred_loss.detach()
+        return self._stats

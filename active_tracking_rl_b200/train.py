@@ -131,8 +131,22 @@ class Trainer(object):
         # capture only records, so the counters below are untouched until the first replay)
         step0, iter0, nsteps0 = self.optimizer.step_count, self.n_iter, self.player.n_steps
         l0 = self.env.lib.track2d_launch_count()
-        with torch.cuda.graph(self._graph, stream=side):
-            self._graph_out = self.iteration(mode)
+        self._graph_apply = None
+        if self.world_size == 1:
+            with torch.cuda.graph(self._graph, stream=side):
+                self._graph_out = self.iteration(mode)
+        else:
+            # multi-GPU: two graphs with the NCCL all-reduce launched eagerly between them (capturing the collective itself
+            # dead-locked on this image): [rollout, losses, backward] | all-reduce | [SharedAdam, state hand-over]
+            p = self.player
+            with torch.cuda.graph(self._graph, stream=side):
+                p.update_rnn_hiden()
+                for _ in range(self.args.num_steps):
+                    p.action_train()
+                self._graph_out = p.optimize(None, self.optimizer, self.model, mode, None, world_size=self.world_size, allreduce=None, apply=False)
+            self._graph_apply = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph_apply, stream=side, pool=self._graph.pool()):
+                p.apply_update(self.optimizer, self.world_size, None, skip_allreduce=True)
         self.launches_per_replay = int(self.env.lib.track2d_launch_count() - l0)  # libtrack2d kernels inside one replay
         self.optimizer.step_count, self.n_iter, self.player.n_steps = step0, iter0, nsteps0
         self._graph_mode = mode
@@ -142,6 +156,9 @@ class Trainer(object):
         """one captured iteration; returns the same tensors as iteration() (overwritten by the next replay)"""
         self.optimizer.advance_for_replay()
         self._graph.replay()
+        if self._graph_apply is not None:
+            self.allreduce(self.optimizer.fp.grad)
+            self._graph_apply.replay()
         self.n_iter += 1
         self.player.n_steps += self.args.num_steps * self.args.num_envs
         return self._graph_out

@@ -261,18 +261,28 @@ def run_gpu_arm(a):
     # ---- the full path --------------------------------------------------------------------------------
     args = default_args(env=ENV_ID, num_envs=E, num_steps=T, seed=1)
     tr = Trainer(args, dev, rank, world)
-    # Single GPU: the whole iteration (4,300 launches) is replayed as ONE CUDA graph unless --no-graph.  Multi-GPU runs
-    # launch eagerly: capturing the NCCL all-reduce inside the graph dead-locked on this image (torch 2.11 / NCCL 2.28),
-    # and at 65,536 envs per GPU the step is GPU-bound anyway (graph replay is worth ~5 % there).
+    # The whole iteration (~3,700 launches) is replayed from CUDA graphs unless --no-graph: ONE graph on a single GPU; with
+    # several GPUs two graphs with the NCCL all-reduce launched eagerly between them (capturing the collective itself dead-locked
+    # on this image, torch 2.11 / NCCL 2.28).
     step_fn, mode = tr.iteration, "eager launches"
-    if not a.no_graph and world == 1:
+    if not a.no_graph:
+        ok = 1
         try:
             tr.capture(warmup=2)
-            step_fn, mode = tr.replay, "one CUDA graph replay per step"
         except Exception as ex:  # noqa: BLE001
-            if rank == 0:
-                sys.stderr.write("CUDA-graph capture failed (%s); running eagerly\n" % (str(ex).splitlines()[0],))
+            ok = 0
+            sys.stderr.write("rank %d: CUDA-graph capture failed (%s)\n" % (rank, str(ex).splitlines()[0] if str(ex) else repr(ex)))
             torch.cuda.synchronize()
+        if world > 1:  # every rank must take the same path (a re-created Trainer restarts from the initial weights)
+            flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            ok = int(flag.item())
+        if ok:
+            step_fn = tr.replay
+            mode = "one CUDA graph replay per step" if world == 1 else "two CUDA graph replays per step around an eager NCCL all-reduce"
+        else:
+            if rank == 0:
+                sys.stderr.write("running eagerly\n")
             tr = Trainer(args, dev, rank, world)
             step_fn = tr.iteration
     for _ in range(a.warmup):
