@@ -119,6 +119,12 @@ __global__ void __launch_bounds__(THREADS) step_kernel(World w, const int32_t *_
     __shared__ __align__(16) uint32_t sobs[(T2D_ENV_CELLS * N) / 4];
     __shared__ uint32_t spos[N];
 
+    // Programmatic dependent launch: when the previous kernel in the stream is another step (rollouts of scripted targets, the
+    // roofline loop) this grid's CTAs are scheduled while that one drains; nothing is read before the wait, which returns once
+    // the previous grid has completed and flushed.  After a kernel launched the ordinary way both instructions are no-ops.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
     const int tid = threadIdx.x;
     const int env0 = blockIdx.x * N;
     const int nenv = min(N, w.E - env0);
@@ -286,6 +292,23 @@ __global__ void full_obs_kernel(World w, ObsT *__restrict__ obs, const uint8_t *
     }
 }
 
+// launch with the programmatic-stream-serialization attribute (see the head of step_kernel)
+template <typename Kernel, typename... Args>
+cudaError_t launch_pdl(Kernel kernel, int grid, int threads, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    static const bool pdl = getenv("T2D_STEP_NO_PDL") == nullptr;  // A/B switch for profiles/
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 template <int TARGET, int RNG, typename ObsT>
 cudaError_t launch_step_t(const World &w, const int32_t *actions, ObsT *obs, float *reward, uint8_t *done, cudaStream_t s) {
     // 16 envs per CTA of 128 threads: 104 four-row groups -> at most one group per thread (a single load latency in
@@ -303,12 +326,11 @@ cudaError_t launch_step_t(const World &w, const int32_t *actions, ObsT *obs, flo
     const int force = T2D_STEP_FORCE_N;
     if (force == 32 || (force == 0 && w.E > wave16 && w.E <= wave32)) {
         constexpr int N = 32, T = 128;
-        step_kernel<TARGET, RNG, ObsT, N, T><<<(w.E + N - 1) / N, T, 0, s>>>(w, actions, obs, reward, done);
+        return launch_pdl(step_kernel<TARGET, RNG, ObsT, N, T>, (w.E + N - 1) / N, T, s, w, actions, obs, reward, done);
     } else {
         constexpr int N = 16, T = 128;
-        step_kernel<TARGET, RNG, ObsT, N, T><<<(w.E + N - 1) / N, T, 0, s>>>(w, actions, obs, reward, done);
+        return launch_pdl(step_kernel<TARGET, RNG, ObsT, N, T>, (w.E + N - 1) / N, T, s, w, actions, obs, reward, done);
     }
-    return cudaGetLastError();
 }
 
 template <typename ObsT>

@@ -239,7 +239,7 @@ def run_gpu_arm(a):
         roofline = {"bound": "hbm", "kernel": "step_kernel<learned target, f32 obs, 16 envs/CTA>", "achieved": round(achieved, 1), "peak": peak,
                     "unit": "GB/s", "frac": round(achieved / peak, 4), "peak_source": peak_src, "us_per_launch": round(k_ms * 1e3, 2),
                     "bytes_per_launch": BYTES_PER_ENV_STEP * E, "traffic": a.traffic_bytes,
-                    "timing": "CUDA events round %d back-to-back launches on the launching stream, obs ring of %d buffers (> L2)" % (n_l, ring)}
+                    "timing": "CUDA events round %d back-to-back launches on the launching stream (programmatic dependent launch between them), obs ring of %d buffers (> L2)" % (n_l, ring)}
         env.close()
         env = Track2DVecEnv(ENV_ID, num_envs=E, device=dev, seed=1, rng="philox", auto_reset=True)
         env.reset()
