@@ -313,9 +313,9 @@ template <int TARGET, int RNG, typename ObsT>
 cudaError_t launch_step_t(const World &w, const int32_t *actions, ObsT *obs, float *reward, uint8_t *done, cudaStream_t s) {
     // 16 envs per CTA of 128 threads: 104 four-row groups -> at most one group per thread (a single load latency in
     // phase B), 5.4 KB of staging, 16 CTAs (2048 threads) resident per SM = 37,888 envs per wave on 148 SMs.
-    // A CTA lives ~10 us (three dependent memory latencies), so batches between one and two waves (e.g. 65,536 envs =
-    // 1.73 waves) pay for two: those run 32 envs per CTA instead (two groups per thread, still 16 CTAs/SM resident,
-    // 75,776 envs per wave) and finish in ONE wave.  Large batches keep 16/CTA (96 % of the HBM roofline at 1 M envs).
+    // A 32-envs-per-CTA variant (65,536 envs in ONE wave instead of 1.73) was 1 % faster without programmatic dependent
+    // launch and is 3.5 % slower with it (20.84 vs 20.11 us: the next step's CTAs now fill the tail of this one), so it is
+    // only kept behind T2D_STEP_FORCE_N=32.  Large batches: 96 % of the HBM roofline at 1 M envs.
     static int sms = 0;
     if (sms == 0) {
         int dev = 0;
@@ -323,8 +323,9 @@ cudaError_t launch_step_t(const World &w, const int32_t *actions, ObsT *obs, flo
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
     const long wave16 = (long)sms * 16 * 16, wave32 = (long)sms * 16 * 32;
-    const int force = T2D_STEP_FORCE_N;
-    if (force == 32 || (force == 0 && w.E > wave16 && w.E <= wave32)) {
+    static const int force = getenv("T2D_STEP_FORCE_N") ? atoi(getenv("T2D_STEP_FORCE_N")) : T2D_STEP_FORCE_N;  // tuning switch
+    (void)wave16; (void)wave32;
+    if (force == 32) {
         constexpr int N = 32, T = 128;
         return launch_pdl(step_kernel<TARGET, RNG, ObsT, N, T>, (w.E + N - 1) / N, T, s, w, actions, obs, reward, done);
     } else {
