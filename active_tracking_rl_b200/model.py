@@ -140,6 +140,27 @@ def weights_init(m):
         m.bias.zero_()
 
 
+def _heads(hx, *linears):
+    """the 4- / 1-wide output heads of one agent (actor, critic[, reward_aux]) on the recurrent state.  On the GPU they are ONE
+    GEMM against the concatenated weights, zero-padded to 8 rows (cuBLAS ran each head's dW = dy^T h over 65,536 rows as a
+    107 us SIMT kernel); the parameters stay separate tensors, so state_dict files are unchanged."""
+    if GEMM_IMPL == "tf32x3" and hx.is_cuda:
+        from . import gemm
+        n = sum(l.weight.shape[0] for l in linears)
+        pad = (-n) % 8
+        ws, bs = [l.weight for l in linears], [l.bias for l in linears]
+        if pad:
+            ws.append(hx.new_zeros((pad, hx.shape[1])))
+            bs.append(hx.new_zeros(pad))
+        out = gemm.linear(hx, torch.cat(ws, 0), torch.cat(bs, 0))
+        res, o = [], 0
+        for l in linears:
+            res.append(out[:, o:o + l.weight.shape[0]])
+            o += l.weight.shape[0]
+        return res
+    return [l(hx) for l in linears]
+
+
 class CNN_maze(nn.Module):
     """perception.py:68-92.  `frames` observations per env are run through the convs as separate images
     and their features concatenated before fc (the reference gets that from view(1, -1) over the
@@ -221,8 +242,8 @@ class A3C(nn.Module):
     def forward(self, x, hx, cx, test=False, forced=None):
         feature = self.encoder(x)
         hx, cx = _lstm_cell(self.lstm, feature, hx, cx)
-        value = self.critic(hx)
-        action, entropy, log_prob = sample_action(self.actor(hx), test, forced)
+        logit, value = _heads(hx, self.actor.actor_linear, self.critic.critic_linear)
+        action, entropy, log_prob = sample_action(logit, test, forced)
         return value, action, entropy, log_prob, hx, cx
 
 
@@ -246,9 +267,9 @@ class TAT(nn.Module):
     def forward(self, x, hx, cx, action_tracker_onehot, test=False, forced=None):
         feature = self.encoder(x) + self.fc_action_tracker(action_tracker_onehot)
         hx, cx = _lstm_cell(self.lstm, feature, hx, cx)
-        value = self.critic(hx)
-        action, entropy, log_prob = sample_action(self.actor(hx), test, forced)
-        return value, action, entropy, log_prob, hx, cx, self.reward_aux(hx)
+        logit, value, r_pred = _heads(hx, self.actor.actor_linear, self.critic.critic_linear, self.reward_aux)
+        action, entropy, log_prob = sample_action(logit, test, forced)
+        return value, action, entropy, log_prob, hx, cx, r_pred
 
 
 class A3C_Dueling(nn.Module):
