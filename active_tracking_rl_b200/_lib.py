@@ -74,6 +74,8 @@ SYMBOLS = {
     "track2d_lstm_bias_workspace_floats": (C.c_int64, [_i64, _i32]),
     "track2d_lstm_cell_forward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i32, _vp]),
     "track2d_lstm_cell_backward": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp]),
+    "track2d_colsum_workspace_floats": (C.c_int64, [_i64, _i32]),
+    "track2d_colsum": (C.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _i64, _vp]),
     "track2d_sharedadam_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _dbl, _dbl, _dbl, _dbl, _dbl, _dbl, _vp, _vp, _vp]),
 }
 

@@ -121,13 +121,54 @@ __global__ void __launch_bounds__(THREADS) lstm_cell_bwd_kernel(const float *__r
     }
 }
 
-// db[j] = sum over CTAs of bias_part[cta][j], in CTA order
+// db[j] = sum over CTAs of bias_part[cta][j]: 32 columns per block, 8 interleaved slices of the partials per column, combined
+// in a fixed order
 __global__ void __launch_bounds__(256) lstm_bias_reduce_kernel(const float *__restrict__ part, int n_part, int n, float *__restrict__ db) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
+    __shared__ float red[8][32];
+    const int col = blockIdx.x * 32 + (threadIdx.x & 31), slice = threadIdx.x >> 5;
     float t = 0.f;
-    for (int p = 0; p < n_part; ++p) t += part[(long long)p * n + j];
-    db[j] = t;
+    if (col < n)
+        for (int p = slice; p < n_part; p += 8) t += part[(long long)p * n + col];
+    red[slice][threadIdx.x & 31] = t;
+    __syncthreads();
+    if (slice == 0 && col < n) {
+#pragma unroll
+        for (int s2 = 1; s2 < 8; ++s2) t += red[s2][threadIdx.x];
+        db[col] = t;
+    }
+}
+
+// out[n] = sum_m x[m][n] for a tall row-major matrix (bias gradients of the Linear layers): thread = (row slot, 4 columns),
+// per-CTA partials, then lstm_bias_reduce_kernel -- fixed summation order
+__global__ void __launch_bounds__(THREADS) colsum_partial_kernel(const float *__restrict__ x, long long ld, long long M, int N, float *__restrict__ part) {
+    const int cpr = N >> 2, rpb = THREADS / cpr;
+    const int chunk = threadIdx.x % cpr, rloc = threadIdx.x / cpr;
+    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (rloc < rpb)
+        for (long long row = (long long)blockIdx.x * rpb + rloc; row < M; row += (long long)gridDim.x * rpb) {
+            const float4 v = ld4(x + row * ld + 4 * chunk);
+            sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+        }
+    __shared__ float4 red[THREADS];
+    red[threadIdx.x] = sum;
+    __syncthreads();
+    if (rloc == 0) {
+        float4 t = red[chunk];
+        for (int r = 1; r < rpb; ++r) {
+            const float4 u = red[r * cpr + chunk];
+            t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+        }
+        st4(part + (long long)blockIdx.x * N + 4 * chunk, t);
+    }
+}
+
+int colsum_grid(long long M, int N) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long rpb = THREADS / (N / 4), groups = (M + rpb - 1) / rpb;
+    const long long g = (long long)sms * 4;
+    return (int)(groups < g ? groups : g);
 }
 
 int lstm_grid(long long E, int H) {
@@ -191,10 +232,38 @@ extern "C" int track2d_lstm_cell_backward(const float *dhy_dev, int64_t dhy_stri
     }
     lstm_cell_bwd_kernel<128><<<grid, THREADS, 0, (cudaStream_t)stream>>>(dhy_dev, dhy_stride, dcy_dev, dcy_stride, cx_dev, cx_stride, cy_dev, act_dev,
                                                                          dgates_dev, dcx_dev, workspace_dev, E);
-    lstm_bias_reduce_kernel<<<(4 * H + 255) / 256, 256, 0, (cudaStream_t)stream>>>(workspace_dev, grid, 4 * H, dbias_dev);
+    lstm_bias_reduce_kernel<<<(4 * H + 31) / 32, 256, 0, (cudaStream_t)stream>>>(workspace_dev, grid, 4 * H, dbias_dev);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         t2d_set_error("track2d_lstm_cell_backward: %s", cudaGetErrorString(e));
+        return T2D_E_CUDA;
+    }
+    t2d_count_launches(2);
+    return T2D_OK;
+}
+
+extern "C" int64_t track2d_colsum_workspace_floats(int64_t M, int32_t N) {
+    if (M <= 0 || N < 4 || N > 1024 || (N & (N - 1))) return 0;
+    return (int64_t)colsum_grid(M, N) * N;
+}
+
+extern "C" int track2d_colsum(const float *x_dev, int64_t ld, int64_t M, int32_t N, float *out_dev, float *workspace_dev, int64_t workspace_floats,
+                              void *stream) {
+    if (!x_dev || !out_dev || !workspace_dev || M <= 0 || N < 4 || N > 1024 || (N & (N - 1)) || ld % 4 || bad_ptr(x_dev) || bad_ptr(out_dev) ||
+        bad_ptr(workspace_dev)) {
+        t2d_set_error("track2d_colsum: N must be a power of two in [4, 1024], buffers 16-byte aligned, ld a multiple of 4");
+        return T2D_E_INVALID;
+    }
+    const int grid = colsum_grid(M, N);
+    if (workspace_floats < (int64_t)grid * N) {
+        t2d_set_error("track2d_colsum: workspace of %lld floats needed (track2d_colsum_workspace_floats)", (long long)grid * N);
+        return T2D_E_INVALID;
+    }
+    colsum_partial_kernel<<<grid, THREADS, 0, (cudaStream_t)stream>>>(x_dev, ld, M, N, workspace_dev);
+    lstm_bias_reduce_kernel<<<(N + 31) / 32, 256, 0, (cudaStream_t)stream>>>(workspace_dev, grid, N, out_dev);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        t2d_set_error("track2d_colsum: %s", cudaGetErrorString(e));
         return T2D_E_CUDA;
     }
     t2d_count_launches(2);

@@ -59,6 +59,23 @@ def supported(x, weight):
             and weight.is_contiguous() and x.data_ptr() % 16 == 0 and weight.data_ptr() % 16 == 0)
 
 
+def colsum(x):
+    """x.sum(0) of a tall contiguous (M, N) matrix in a fixed summation order (csrc/track2d_lstm.cu); torch's own for widths the
+    kernel does not take"""
+    M, N = x.shape
+    if not (x.is_cuda and x.dtype == torch.float32 and 4 <= N <= 1024 and (N & (N - 1)) == 0 and x.stride(1) == 1 and x.stride(0) % 4 == 0
+            and x.data_ptr() % 16 == 0):
+        return x.sum(0)
+    lib = _lib.load()
+    key = (x.device.index, "colsum", M, N)
+    ws = _WS.get(key)
+    if ws is None:
+        ws = _WS[key] = torch.empty(int(lib.track2d_colsum_workspace_floats(M, N)), dtype=torch.float32, device=x.device)
+    out = torch.empty(N, dtype=torch.float32, device=x.device)
+    _lib.check(lib.track2d_colsum(_p(x), x.stride(0), M, N, _p(out), _p(ws), ws.numel(), C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)), lib)
+    return out
+
+
 class _Linear(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, relu):
@@ -83,7 +100,7 @@ class _Linear(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             gw = gemm(gy, True, N, x, True, x.stride(0), N, K, M)               # dW[n, k] = sum_m dy[m, n] x[m, k]
         if ctx.needs_input_grad[2]:
-            gb = gy.sum(0)
+            gb = colsum(gy)
         return gx, gw, gb, None
 
 

@@ -265,7 +265,7 @@ class TAT(nn.Module):
             self.lstm.bias_hh.zero_()
 
     def forward(self, x, hx, cx, action_tracker_onehot, test=False, forced=None):
-        feature = self.encoder(x) + self.fc_action_tracker(action_tracker_onehot)
+        feature = self.encoder(x) + _linear(action_tracker_onehot, self.fc_action_tracker)
         hx, cx = _lstm_cell(self.lstm, feature, hx, cx)
         logit, value, r_pred = _heads(hx, self.actor.actor_linear, self.critic.critic_linear, self.reward_aux)
         action, entropy, log_prob = sample_action(logit, test, forced)

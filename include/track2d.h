@@ -223,6 +223,12 @@ int track2d_lstm_cell_backward(const float *dhy_dev, int64_t dhy_stride, const f
                                int64_t cx_stride, const float *cy_dev, const float *act_dev, float *dgates_dev, float *dcx_dev,
                                float *dbias_dev, float *workspace_dev, int64_t workspace_floats, int64_t E, int32_t H, void *stream);
 
+/* out[n] = sum_m x[m*ld + n] (bias gradient of a Linear layer: the reference's autograd sums dy over the batch).  N a power of
+ * two in [4, 1024]; workspace of track2d_colsum_workspace_floats(M, N) floats; fixed summation order. */
+int64_t track2d_colsum_workspace_floats(int64_t M, int32_t N);
+int track2d_colsum(const float *x_dev, int64_t ld, int64_t M, int32_t N, float *out_dev, float *workspace_dev, int64_t workspace_floats,
+                   void *stream);
+
 #ifdef __cplusplus
 }
 #endif

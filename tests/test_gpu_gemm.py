@@ -101,3 +101,14 @@ def test_lstm_pointwise_matches_torch_lstmcell():
         assert torch.allclose(a, b, rtol=1e-4, atol=1e-5 * float(b.abs().max()) + 1e-6)
     got3 = torch.autograd.grad(G.lstm_pointwise(ig, hg, cx, b_ih, b_hh)[0], ins, gh[:, 0])
     assert torch.equal(got2[3], got3[3])
+
+
+@pytest.mark.parametrize("M,N", [(65536, 256), (1000, 8), (7, 512), (4096, 1024), (300, 12)])
+def test_colsum_matches_torch(M, N):
+    from active_tracking_rl_b200 import gemm as G
+    g = torch.Generator(device="cuda:0").manual_seed(5)
+    x = torch.randn(M, N, generator=g, device="cuda:0")
+    out = G.colsum(x)  # N = 12 is not a power of two: torch's own sum
+    ref = x.double().sum(0)
+    assert torch.allclose(out.double(), ref, rtol=1e-5, atol=1e-4 * float(M) ** 0.5)
+    assert torch.equal(out, G.colsum(x))
