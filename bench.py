@@ -366,9 +366,9 @@ def main():
     ap.add_argument("--fp32-emulation", action="store_true",
                     help="route the policy's fp32 GEMMs through cuBLAS 12.9 BF16x9 emulation (fp32-accurate, tensor cores); off = SIMT SGEMM")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying one CUDA graph per step")
-    ap.add_argument("--traffic-bytes", type=float, default=60907008.0,
+    ap.add_argument("--traffic-bytes", type=float, default=56198400.0,
                     help="dram__bytes_read.sum + dram__bytes_write.sum per step-kernel launch from the committed ncu capture "
-                         "(profiles/ncu_r1_kernels.txt: 27.46 MB read + 33.44 MB written INSIDE the kernel; the 126 MB write-back L2 "
+                         "(profiles/ncu_r1_step_kernel_pdl.txt: 24.46 MB read + 31.74 MB written INSIDE the kernel; the 126 MB write-back L2 "
                          "retires the rest of the 88.6 MB of observations after the kernel ends)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
