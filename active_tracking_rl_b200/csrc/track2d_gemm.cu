@@ -476,6 +476,8 @@ Plan make_plan(int64_t M, int64_t N, int64_t K) {
     pl.sm = tiles_m >= 2 ? 2 : 1;
     pl.sn = tiles_n >= 2 ? 2 : 1;
     if (pl.sm == 1 && pl.sn == 2) pl.sn = 1;  // (1,2) is not instantiated; one tile per CTA then
+    static const int64_t narrow_k = getenv("T2D_GEMM_NARROW_K") ? atoll(getenv("T2D_GEMM_NARROW_K")) : 128;  // tuning switch
+    if (K <= narrow_k && pl.sn == 2) pl.sn = 1;  // short reductions: 2x1 super-tiles keep the TMEM double buffer (epilogue overlap)
     pl.st_m = (tiles_m + pl.sm - 1) / pl.sm;
     pl.st_n = (tiles_n + pl.sn - 1) / pl.sn;
     pl.nkb = (int)((K + BK - 1) / BK);
