@@ -23,7 +23,8 @@
 // TMEM accumulators (128 lanes x 128 columns each): a 16-deep reduction block stages SM tiles of A and SN tiles of B once and
 // feeds SM*6 MMAs of N = 128*SN, which halves the L2 -> SM operand traffic per flop against one tile per CTA (that traffic, not the
 // tensor pipe, bounded the one-tile version: measured).  With <= 2 accumulators per super-tile the TMEM allocation is
-// double-buffered so the epilogue overlaps the next super-tile.  Two 64 KB operand stages + three 32 KB raw stages of shared memory.  Split-K (weight
+// double-buffered so the epilogue overlaps the next super-tile.  Two 64 KB operand stages + two 32 KB raw stages of shared memory;
+// the epilogue transposes 32 x 32 blocks through 18 KB of staging so that its global stores are full 128-byte row segments.  Split-K (weight
 // gradients: the reduction runs over the env axis) writes partial tiles to a workspace; a second kernel sums them in a fixed
 // order, so results are bit-reproducible run to run.
 #include <cuda_runtime.h>
@@ -39,7 +40,7 @@ namespace {
 
 constexpr int BM = 128, BN = 128, BK = 16;
 constexpr int STAGES = 2;      // MMA operand stages (hi/lo tiles in the UMMA layouts)
-constexpr int RAW_STAGES = 3;  // cp.async landing ring of raw fp32 chunks (each thread re-reads only what it copied itself)
+constexpr int RAW_STAGES = 2;  // cp.async landing ring of raw fp32 chunks (each thread re-reads only what it copied itself)
 constexpr int TILE_BYTES = BM * BK * 4;      // 8 KB: one 128 x 16 fp32 operand tile (BM == BN)
 constexpr int SLOT_BYTES = 2 * TILE_BYTES;   // hi | lo
 constexpr int MAX_SLOTS = 4;                 // SM + SN <= 4 operand tiles per stage
@@ -49,7 +50,9 @@ constexpr int THREADS = (EPI_WARPS + 1 + PROD_WARPS) * 32;  // 672
 constexpr int PROD_THREADS = PROD_WARPS * 32;               // 512 = the 16-byte chunks of one operand tile
 constexpr int TMEM_COLS = 512;
 constexpr int RAW_BYTES = MAX_SLOTS * TILE_BYTES;       // 32 KB
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + RAW_STAGES * RAW_BYTES + 1024 /* alignment slack */ + 128 /* barriers */;
+constexpr int EPI_PITCH = 36;                            // floats per staged row: 32 columns + 4 (16-byte aligned, conflict-free both ways)
+constexpr int EPI_BYTES = 32 * EPI_PITCH * 4;            // one warp's 32 x 32 staging tile
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + RAW_STAGES * RAW_BYTES + 4 * EPI_BYTES + 1024 /* alignment slack */ + 128 /* barriers */;
 static_assert(BM * BK / 4 == PROD_THREADS, "one chunk per producer thread per operand tile");
 
 struct GemmParams {
@@ -253,7 +256,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const GemmParam
     static_assert(SM + SN <= MAX_SLOTS && NACC * BN <= TMEM_COLS, "super-tile does not fit");
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzle atoms need aligned tiles
-    const uint32_t bars = smem0 + STAGES * STAGE_BYTES;
+    const uint32_t epi0 = smem0 + STAGES * STAGE_BYTES + RAW_STAGES * RAW_BYTES;  // epilogue staging, one 32 x 32 tile per warp
+    const uint32_t bars = epi0 + EPI_WARPS * EPI_BYTES;
     // barriers: full[STAGES], empty[STAGES], acc_full[2], acc_empty[2]; then the TMEM base address
     const uint32_t bar_full = bars, bar_empty = bars + 8 * STAGES, bar_accf = bars + 16 * STAGES, bar_acce = bar_accf + 16;
     const uint32_t tmem_slot = bar_acce + 16;
@@ -316,7 +320,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const GemmParam
 #pragma unroll
         for (int i = 0; i < RAW_STAGES - 1; ++i) issue();
         for (int it = 0; it < n_issued; ++it) {
-            issue();                                                                    // RAW_STAGES - 1 blocks ahead
+            issue();                                                                    // RAW_STAGES - 1 block(s) ahead
             asm volatile("cp.async.wait_group %0;" ::"n"(RAW_STAGES - 1) : "memory");  // block `it` has landed
             const int s = it % STAGES;
             mbar_wait(bar_empty + 8 * s, ((it / STAGES) & 1) ^ 1);
@@ -380,11 +384,12 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const GemmParam
             mbar_wait_backoff(bar_accf + 8 * buf, use & 1);
             tc_fence_after();
             const bool fused = p.splits == 1;
+            const uint32_t stg = epi0 + warp * EPI_BYTES;
+            float *dbase = p.D + (long long)w.sp * p.split_stride;
 #pragma unroll 1
             for (int ij = 0; ij < NACC; ++ij) {
                 const int i = ij / SN, j = ij % SN;
-                const int row = w.m0 + i * BM + warp * 32 + lane;
-                float *drow = p.D + (long long)w.sp * p.split_stride + (long long)row * p.ldd;
+                const int row0 = w.m0 + i * BM + warp * 32;
 #pragma unroll 1
                 for (int c = 0; c < BN / 32; ++c) {
                     const int col0 = w.n0 + j * BN + c * 32;
@@ -392,24 +397,32 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const GemmParam
                     uint32_t r[32];
                     tc_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)((buf * NACC + ij) * BN + c * 32), r);
                     tc_wait_ld();
-                    if (row < p.M) {
+                    // thread = row: + bias, ReLU, then through the staging tile so that every global store instruction of the warp
+                    // writes four full 128-byte row segments (a thread-per-row store touches 32 different lines per instruction)
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const int col = col0 + 4 * q;
-                            if (col < p.N) {
-                                float4 v = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
-                                                       __uint_as_float(r[4 * q + 3]));
-                                if (fused) {
-                                    if (p.bias) {
-                                        const float4 bv = __ldg(reinterpret_cast<const float4 *>(p.bias + col));
-                                        v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
-                                    }
-                                    if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-                                }
-                                *reinterpret_cast<float4 *>(drow + col) = v;
+                    for (int q = 0; q < 8; ++q) {
+                        float4 v = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
+                                               __uint_as_float(r[4 * q + 3]));
+                        const int col = col0 + 4 * q;
+                        if (fused && col < p.N) {
+                            if (p.bias) {
+                                const float4 bv = __ldg(reinterpret_cast<const float4 *>(p.bias + col));
+                                v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
                             }
+                            if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
                         }
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg + (uint32_t)(lane * EPI_PITCH + 4 * q) * 4u), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
                     }
+                    __syncwarp();
+                    const int col = col0 + 4 * (lane & 7);
+#pragma unroll
+                    for (int it8 = 0; it8 < 8; ++it8) {
+                        const int rl = 4 * it8 + (lane >> 3), row = row0 + rl;
+                        float4 v;
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(stg + (uint32_t)(rl * EPI_PITCH + 4 * (lane & 7)) * 4u) : "memory");
+                        if (row < p.M && col < p.N) *reinterpret_cast<float4 *>(dbase + (long long)row * p.ldd + col) = v;
+                    }
+                    __syncwarp();
                 }
             }
             tc_fence_before();
