@@ -12,13 +12,14 @@
 // the result carries fp32 accuracy -- unlike plain TF32, which loses 13 mantissa bits of every input.
 //
 // Structure (one persistent CTA per SM, 21 warps, warp-specialised):
-//   warps 5..20  producers   cp.async 16-byte chunks into a 3-deep raw ring (two reduction blocks in flight), then each thread
+//   warps 5..20  producers   cp.async 16-byte chunks into a 2-deep raw ring (the next reduction block in flight), then each thread
 //                            re-reads its own chunks, splits them hi/lo and st.shared's them into the UMMA canonical swizzled layouts (K-major or MN-major, so the same kernel
 //                            runs y = x W^T, dx = dy W and dW = dy^T x without any transposed copy), fence.proxy.async +
 //                            mbarrier arrive
 //   warp 4       MMA issuer  one lane issues the tcgen05.mma's (128 x 256 x 8 each for 2-wide super-tiles); tcgen05.commit releases the
 //                            shared-memory stage / publishes the accumulators
-//   warps 0..3   epilogue    tcgen05.ld (32 lanes x 32 columns per warp), + bias, ReLU, 16-byte global stores
+//   warps 0..3   epilogue    tcgen05.ld (32 lanes x 32 columns per warp), + bias, ReLU, transpose through shared memory,
+//                            16-byte global stores that cover full 128-byte row segments
 // A CTA works on a SUPER-TILE of SM x SN output tiles of 128 x 128 (2x2, or 2x1 / 1x1 for narrow outputs) held in SM*SN
 // TMEM accumulators (128 lanes x 128 columns each): a 16-deep reduction block stages SM tiles of A and SN tiles of B once and
 // feeds SM*6 MMAs of N = 128*SN, which halves the L2 -> SM operand traffic per flop against one tile per CTA (that traffic, not the
