@@ -86,3 +86,20 @@ def test_unsupported_configurations_fail_loudly():
         build_model(OBS, ACT, default_args(network="cnn-lstm"), torch.device("cpu"))
     with pytest.raises(NotImplementedError):
         build_model(OBS, ACT, default_args(network="maze-lstm-continuous"), torch.device("cpu"))
+
+
+def test_fused_heads_and_linear_fall_back_to_torch_on_cpu():
+    """model._heads / model._linear / gemm.colsum take torch's own ops for CPU tensors (host-side tests never touch the CUDA
+    library) and return exactly what the separate nn.Linear modules do"""
+    import torch
+    from active_tracking_rl_b200 import gemm, model as M
+    torch.manual_seed(0)
+    actor, critic, aux = torch.nn.Linear(128, 4), torch.nn.Linear(128, 1), torch.nn.Linear(128, 1)
+    hx = torch.randn(6, 128)
+    logit, value, r = M._heads(hx, actor, critic, aux)
+    assert torch.equal(logit, actor(hx)) and torch.equal(value, critic(hx)) and torch.equal(r, aux(hx))
+    fc = torch.nn.Linear(512, 256)
+    x = torch.randn(6, 512)
+    assert torch.equal(M._linear(x, fc, relu=True), torch.relu(fc(x)))
+    assert torch.equal(gemm.colsum(x), x.sum(0))
+    assert not gemm.supported(x, fc.weight)
