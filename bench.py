@@ -7,7 +7,10 @@
 A "step" is one pass of the whole hot path over the batch: a 20-step rollout of E envs per GPU
 (policy.step <-> env.step on one stream, no host round trip) followed by one update (bootstrap, GAE,
 A3C losses of tracker + TAT target + aux reward head, backward, [NCCL all-reduce], fused SharedAdam):
-E * 20 env-steps per GPU.  The JSON line carries:
+E * 20 env-steps per GPU.  The step is replayed from CUDA graphs (one graph on a single GPU; two graphs around an
+eagerly launched all-reduce with several).  The policy computes in float32: fc / LSTM / head GEMMs on the tcgen05
+tensor cores with the fp32-accurate 3xTF32 split, conv stack / LSTM cell / GAE / SharedAdam as hand-written kernels.
+The JSON line carries:
 
   value / ms_per_step   whole-job env-steps/s (all GPUs), device-timed with CUDA events, max over ranks
   env_only              the environment alone (step kernel + auto-reset, resident random actions)
