@@ -31,14 +31,16 @@ def env_only(env_id, E, steps=200, warmup=60):
 
 
 def train(env_id, E, iters=5, **kw):
+    """rollout + update iterations replayed from one CUDA graph (what bench.py does on a single GPU)"""
     tr = Trainer(default_args(env=env_id, num_envs=E, **kw), "cuda:0")
-    for _ in range(3):
-        tr.iteration()
+    tr.capture(warmup=3)
+    for _ in range(2):
+        tr.replay()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(iters):
-        tr.iteration()
+        tr.replay()
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
