@@ -19,8 +19,8 @@
 
 struct __align__(16) HeapEntry {  // one 16-byte shared-memory access per heap slot
     double f;
-    uint32_t c;  // cell | g << 16
-    uint32_t pad;
+    uint32_t c;   // cell | g << 16
+    uint32_t rc;  // row << 8 | col of the cell (saves the division by the map width on every pop)
 };
 
 struct AStarScratch {
@@ -45,9 +45,11 @@ struct HeapView {
     }
 };
 
-// [f, node] < [f2, node2]
+// [f, node] < [f2, node2].  f = g + distance is a non-negative finite double, so its bit pattern orders like the value: integer
+// compares instead of two FP64 predicate instructions on the critical path of every sift level.
 __device__ __forceinline__ bool heap_lt(const HeapEntry &a, const HeapEntry &b) {
-    return a.f != b.f ? a.f < b.f : (a.c >> 16) < (b.c >> 16);
+    const long long fa = __double_as_longlong(a.f), fb = __double_as_longlong(b.f);
+    return fa != fb ? fa < fb : (a.c >> 16) < (b.c >> 16);
 }
 
 template <bool FAST>
@@ -113,35 +115,39 @@ __device__ int astar_plan(const World &w, int e, const uint32_t *bm, AStarScratc
         HeapEntry en;
         en.f = 0.0 + __dsqrt_rn(__dadd_rn(__dmul_rn(dr, dr), __dmul_rn(dc, dc)));
         en.c = (uint32_t)start;
-        en.pad = 0;
+        en.rc = ((uint32_t)sr << 8) | (uint32_t)sc;
         a.heap[0] = en;
         hn = 1;
     }
     int sol = -1;
     for (;;) {
-        uint32_t top = 0xFFFFFFFFu;  // heap empty
+        uint32_t top = 0xFFFFFFFFu, top_rc = 0;  // heap empty
         if (lane == 0 && hn > 0) {
             // Frontier.pop == heapq.heappop
             hn--;
             const bool fast = hn < T2D_HEAP_SMEM;
             const HeapEntry last = fast ? hfast.get(hn) : hslow.get(hn);
             top = last.c;
+            top_rc = last.rc;
             if (hn > 0) {
-                top = a.heap[0].c;
+                const HeapEntry first = a.heap[0];
+                top = first.c;
+                top_rc = first.rc;
                 if (fast) hq_siftup(hfast, 0, hn, last);
                 else hq_siftup(hslow, 0, hn, last);
             }
         }
         top = __shfl_sync(0xFFFFFFFFu, top, 0);
+        top_rc = __shfl_sync(0xFFFFFFFFu, top_rc, 0);
         if (top == 0xFFFFFFFFu) break;
         const int cell = (int)(top & 0xFFFFu), g = (int)(top >> 16);
+        const int r = (int)(top_rc >> 8), c = (int)(top_rc & 255u);
         if (cell == goal) { sol = cell; break; }
         // neighbour `lane` (actions 0..3 in the reference's order)
         bool add = false;
         double f = 0.0;
         if (lane < 4) {
             if (lane == 0) a.gcost[cell] |= 0x8000u;  // explored.add (never one of its own neighbours)
-            const int r = cell / W, c = cell - r * W;
             const int nr = r + action_dr(lane), nc = c + action_dc(lane);
             if (!((bm[map_word_index(nr, nc)] >> ((nc + T2D_PAD) & 31)) & 1u)) {  // wall: child == parent, already explored
                 const int child = nr * W + nc;
@@ -162,14 +168,13 @@ __device__ int astar_plan(const World &w, int e, const uint32_t *bm, AStarScratc
 #pragma unroll
         for (int act = 0; act < 4; act++) fa[act] = __shfl_sync(0xFFFFFFFFu, f, act);
         if (lane == 0 && addmask) {
-            const int r = cell / W, c = cell - r * W;
 #pragma unroll
             for (int act = 0; act < 4; act++) {
                 if (!((addmask >> act) & 1u)) continue;
                 HeapEntry en;  // Frontier.add == heappush
                 en.f = fa[act];
                 en.c = (uint32_t)((r + action_dr(act)) * W + c + action_dc(act)) | ((uint32_t)(g + 1) << 16);
-                en.pad = 0;
+                en.rc = ((uint32_t)(r + action_dr(act)) << 8) | (uint32_t)(c + action_dc(act));
                 hn++;
                 if (hn <= T2D_HEAP_SMEM) hq_siftdown(hfast, 0, hn - 1, en);
                 else hq_siftdown(hslow, 0, hn - 1, en);
