@@ -88,12 +88,12 @@ __device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     for (uint32_t spins = 0; !mbar_try(bar, parity); ++spins)
-        if (spins > (1u << 24)) __trap();  // a lost arrival must not hang the device: fail the launch instead
+        if (spins > (1u << 28)) __trap();  // a lost arrival must not hang the device: fail the launch instead (seconds of polling)
 }
 __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {  // long waits (epilogue): leave the issue slots alone
     for (uint32_t spins = 0; !mbar_try(bar, parity); ++spins) {
         __nanosleep(100);
-        if (spins > (1u << 22)) __trap();
+        if (spins > (1u << 26)) __trap();
     }
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
