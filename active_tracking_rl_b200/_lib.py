@@ -59,6 +59,7 @@ SYMBOLS = {
     "track2d_set_ram": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp]),
     "track2d_get_nav": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, _vp]),
     "track2d_set_nav": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "track2d_astar_solve": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, _vp]),
     "track2d_get_rewards_f64": (C.c_int, [_vp, _i32, _i32, _vp]),
     "track2d_get_target_actions": (C.c_int, [_vp, _i32, _i32, _vp]),
     "track2d_seed_env": (C.c_int, [_vp, _i32, _u32]),

@@ -19,6 +19,7 @@ cudaError_t t2d_launch_reset_f32(const World &w, const uint8_t *mask, int from_l
 cudaError_t t2d_launch_reset_u8(const World &w, const uint8_t *mask, int from_list, uint8_t *obs, int init_only, cudaStream_t s);
 cudaError_t t2d_launch_seed_numpy(const World &w, int first, int count, unsigned long long seed, int add_index, cudaStream_t s);
 cudaError_t t2d_launch_nav_replan(const World &w, cudaStream_t s);
+cudaError_t t2d_launch_astar_direct(const World &w, int first, int count, const int32_t *sg_dev, int32_t *len_dev, cudaStream_t s);
 int t2d_nav_slots();
 
 static thread_local char g_err[512] = "";
@@ -535,6 +536,39 @@ int track2d_get_rewards_f64(track2d_env *env, int32_t first, int32_t count, doub
     DeviceGuard guard(env->cfg.device);
     T2D_CUDA(cudaDeviceSynchronize());
     T2D_CUDA(cudaMemcpy(rewards_host, env->w.rew64 + 2 * (size_t)first, (size_t)count * 2 * sizeof(double), cudaMemcpyDeviceToHost));
+    return T2D_OK;
+}
+
+int track2d_astar_solve(track2d_env *env, int32_t first, int32_t count, const int32_t *start_host, const int32_t *goal_host, int32_t *plan_host,
+                        int32_t *len_host) {
+    int rc = check_range(env, first, count);
+    if (rc != T2D_OK) return rc;
+    T2D_REQUIRE(env->w.nav_plan, "astar_solve: not a Nav/RPF env");
+    T2D_REQUIRE(start_host && goal_host && len_host, "astar_solve: start, goal and len are required");
+    DeviceGuard guard(env->cfg.device);
+    T2D_CUDA(cudaDeviceSynchronize());
+    std::vector<int32_t> sg((size_t)count * 4);
+    for (int i = 0; i < count; i++) {
+        sg[4 * i] = start_host[2 * i]; sg[4 * i + 1] = start_host[2 * i + 1];
+        sg[4 * i + 2] = goal_host[2 * i]; sg[4 * i + 3] = goal_host[2 * i + 1];
+        for (int k = 0; k < 4; k++)
+            T2D_REQUIRE(sg[4 * i + k] >= 0 && sg[4 * i + k] < ((k & 1) ? env->w.W : env->w.H), "astar_solve: start / goal outside the map");
+    }
+    int32_t *dbuf = nullptr;
+    T2D_CUDA(cudaMalloc(&dbuf, (size_t)count * 5 * sizeof(int32_t)));
+    cudaError_t err = cudaMemcpy(dbuf, sg.data(), sg.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+    if (err == cudaSuccess) {
+        t2d_count_launches(1);
+        err = t2d_launch_astar_direct(env->w, first, count, dbuf, dbuf + (size_t)count * 4, 0);
+    }
+    if (err == cudaSuccess) err = cudaDeviceSynchronize();
+    if (err == cudaSuccess) err = cudaMemcpy(len_host, dbuf + (size_t)count * 4, (size_t)count * sizeof(int32_t), cudaMemcpyDeviceToHost);
+    cudaFree(dbuf);
+    T2D_CUDA(err);
+    if (plan_host) {
+        std::vector<int32_t> ln(count), idx(count);
+        return track2d_get_nav(env, first, count, plan_host, ln.data(), idx.data(), nullptr);
+    }
     return T2D_OK;
 }
 

@@ -694,6 +694,24 @@ __global__ void __launch_bounds__(32) nav_replan_philox_kernel(World w) {
     }
 }
 
+// AstarSolver.solve (Astar_solver.py:121-149) called directly: plan from (sr, sc) to (gr, gc) on the generator maze of env
+// first + i, for i < count.  The plan lands in that env's Navigator plan buffer (a_i = 0); len_out[i] = its length or -1.
+__global__ void __launch_bounds__(32) astar_direct_kernel(World w, int first, int count, const int32_t *__restrict__ sg, int32_t *__restrict__ len_out) {
+    __shared__ PhiloxNavScratch s;
+    const int lane = threadIdx.x;
+    for (int i = blockIdx.x; i < count; i += gridDim.x) {
+        const int e = first + i;
+        load_gen_maze(w, e, s.bm, lane);
+        const int len = astar_plan(w, e, s.bm, s.astar, blockIdx.x, sg[4 * i], sg[4 * i + 1], sg[4 * i + 2], sg[4 * i + 3], lane);
+        if (lane == 0) {
+            len_out[i] = len;
+            w.nav_meta[e] = (uint32_t)(len > 0 ? len : 0);
+            w.nav_goal[e] = (uint32_t)sg[4 * i + 2] | ((uint32_t)sg[4 * i + 3] << 8);
+        }
+        __syncwarp();
+    }
+}
+
 __global__ void finish_replan_kernel(World w) {
     if (threadIdx.x == 0 && blockIdx.x == 0) w.work_count[1] = 0;
 }
@@ -759,6 +777,10 @@ cudaError_t t2d_launch_nav_replan(const World &w, cudaStream_t s) {
     if (w.rng_mode == T2D_RNG_NUMPY) nav_replan_numpy_kernel<<<T2D_NAV_GRID, 32, 0, s>>>(w);
     else nav_replan_philox_kernel<<<T2D_NAV_GRID, 32, 0, s>>>(w);
     finish_replan_kernel<<<1, 32, 0, s>>>(w);
+    return cudaGetLastError();
+}
+cudaError_t t2d_launch_astar_direct(const World &w, int first, int count, const int32_t *sg_dev, int32_t *len_dev, cudaStream_t s) {
+    astar_direct_kernel<<<min(count, T2D_NAV_GRID), 32, 0, s>>>(w, first, count, sg_dev, len_dev);
     return cudaGetLastError();
 }
 int t2d_nav_slots() { return T2D_NAV_GRID; }

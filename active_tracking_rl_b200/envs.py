@@ -188,6 +188,16 @@ class Track2DVecEnv(object):
         _lib.check(self.lib.track2d_get_nav(self.h, first, count, _np(plan), _np(ln), _np(idx), _np(goal)), self.lib)
         return plan, ln, idx, goal
 
+    def astar_solve(self, start, goal, first=0):
+        """AstarSolver.solve + get_actions (Astar_solver.py:102-149) on the generator maze of env first + i, from start[i] to
+        goal[i]; returns (plans int32 [n][NAV_MAXPLAN], lengths int32 [n], -1 = unreachable).  Overwrites those envs' plans."""
+        start = np.ascontiguousarray(start, np.int32).reshape(-1, 2)
+        goal = np.ascontiguousarray(goal, np.int32).reshape(-1, 2)
+        n = start.shape[0]
+        plan, ln = np.zeros((n, _lib.NAV_MAXPLAN), np.int32), np.zeros(n, np.int32)
+        _lib.check(self.lib.track2d_astar_solve(self.h, first, n, _np(start), _np(goal), _np(plan), _np(ln)), self.lib)
+        return plan, ln
+
     def set_nav(self, plan, length, idx, goal, first=0):
         plan = np.ascontiguousarray(plan, np.int32).reshape(-1, _lib.NAV_MAXPLAN)
         length = np.ascontiguousarray(length, np.int32).reshape(-1)

@@ -149,6 +149,12 @@ int track2d_set_ram(track2d_env *env, int32_t first, int32_t count, const int32_
 /* Navigator.plan_actions / a_i / goal_states (envs/navigator.py:5-63): plan int32 [count][TRACK2D_NAV_MAXPLAN] */
 int track2d_get_nav(track2d_env *env, int32_t first, int32_t count, int32_t *plan_host, int32_t *len_host, int32_t *idx_host, int32_t *goal_host);
 int track2d_set_nav(track2d_env *env, int32_t first, int32_t count, const int32_t *plan_host, const int32_t *len_host, const int32_t *idx_host, const int32_t *goal_host);
+/* AstarSolver(env, goal).solve() + get_actions (envs/Astar_solver.py:102-149) called directly, for known-answer tests: plans from
+ * start_host[i] to goal_host[i] ((row, col), int32 [count][2]) on the generator maze of env first + i.  len_host[i] = number of actions
+ * or -1 when the goal is unreachable; plan_host (may be NULL) int32 [count][TRACK2D_NAV_MAXPLAN].  Overwrites the Navigator plan of
+ * those envs.  Nav / RPF handles only; synchronous. */
+int track2d_astar_solve(track2d_env *env, int32_t first, int32_t count, const int32_t *start_host, const int32_t *goal_host,
+                        int32_t *plan_host, int32_t *len_host);
 /* float64 rewards of the last step, [E][2] (needs T2D_FLAG_KEEP_F64): exactly what Track1v1Env.step returns */
 int track2d_get_rewards_f64(track2d_env *env, int32_t first, int32_t count, double *rewards_host);
 /* the action the target actually executed in the last step (Ram/Nav/RPF override), int32 [count] */

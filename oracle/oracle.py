@@ -74,6 +74,11 @@ def lib():
         L.o_astar.argtypes = [vp, vp, vp, vp, i32]
         L.o_run_random.restype = C.c_long
         L.o_run_random.argtypes = [i32, i32, i32, i32, u32, C.c_long, vp, vp]
+        i64 = C.c_long
+        L.o_batch_pipeline.restype = i64
+        L.o_batch_pipeline.argtypes = [i32, i32, i32, i32, i64, i64, i64, u32, i32] + [vp] * 12 + [i32]
+        L.o_batch_inject_steps.restype = None
+        L.o_batch_inject_steps.argtypes = [i32, i32, i32, i32, i64, i64, i64, i32, i32, i32] + [vp] * 9 + [i32]
         _lib = L
     return _lib
 
@@ -232,3 +237,52 @@ def run_random(env_id, seed, n_steps):
     ne = C.c_long(0)
     n = lib().o_run_random(MAP[m], OBS[o], TARGET[t], lvl, int(seed) & 0xFFFFFFFF, int(n_steps), _p(rs), C.byref(ne))
     return int(n), rs, int(ne.value)
+
+
+def _threads():
+    return max(1, min(os.cpu_count() or 1, 64))
+
+
+def batch_pipeline(env_id, E, seed0, actions, first=0, n=None, want_maze=False):
+    """Env e of an E-wide batch == the reference after np.random.seed(seed0 + e): reset, then T = len(actions) steps
+    with reset-on-done (libtrack2d's auto-reset convention).  ONE ctypes call for the whole batch (threads inside).
+    actions int32 [T][E][2].  Returns a dict of arrays indexed [t][e] (rows outside [first, first + n) stay zero)."""
+    m, o, t, lvl = parse_env_id(env_id)
+    L = lib()
+    actions = np.ascontiguousarray(actions, np.int32)
+    T = actions.shape[0]
+    assert actions.shape == (T, E, 2)
+    n = E - first if n is None else n
+    H = 81 if m == "Maze" else 82
+    cells = H * H if o == "Full" else 169
+    out = dict(
+        reset_obs=np.zeros((E, 2, cells), np.uint8), reset_pos=np.zeros((E, 2, 2), np.int32),
+        reset_maze=np.zeros((E, H, H), np.uint8) if want_maze else None,
+        pos=np.zeros((T, E, 2, 2), np.int32), ctr=np.zeros((T, E, 2), np.int32), rew=np.zeros((T, E, 2), np.float64),
+        done=np.zeros((T, E), np.uint8), tgt_act=np.zeros((T, E), np.int32), obs=np.zeros((T, E, 2, cells), np.uint8),
+        rng_ckpt=np.zeros((E, 9), np.uint32), plan_meta=np.zeros((T, E, 2), np.int32))
+    q = lambda k: _p(out[k]) if out[k] is not None else None  # noqa: E731
+    out["n_done"] = int(L.o_batch_pipeline(MAP[m], OBS[o], TARGET[t], lvl, E, first, n, int(seed0) & 0xFFFFFFFF, T, _p(actions),
+                                           q("reset_obs"), q("reset_maze"), q("reset_pos"), q("pos"), q("ctr"), q("rew"), q("done"),
+                                           q("tgt_act"), q("obs"), q("rng_ckpt"), q("plan_meta"), _threads()))
+    return out
+
+
+def batch_inject_steps(env_id, maze, pos0, ctr0, actions):
+    """T steps (no reset) of E envs from injected states; one ctypes call.  maze uint8 [E][H][W], pos0 int32 [E][2][2],
+    ctr0 int32 [E][2] = (C_far, elapsed), actions int32 [T][E][2]."""
+    m, o, t, lvl = parse_env_id(env_id)
+    L = lib()
+    maze = np.ascontiguousarray(maze, np.uint8)
+    pos0 = np.ascontiguousarray(pos0, np.int32)
+    ctr0 = np.ascontiguousarray(ctr0, np.int32)
+    actions = np.ascontiguousarray(actions, np.int32)
+    E, H, W = maze.shape
+    T = actions.shape[0]
+    assert actions.shape == (T, E, 2) and pos0.shape == (E, 2, 2) and ctr0.shape == (E, 2)
+    cells = H * W if o == "Full" else 169
+    out = dict(pos=np.zeros((T, E, 2, 2), np.int32), ctr=np.zeros((T, E, 2), np.int32), rew=np.zeros((T, E, 2), np.float64),
+               done=np.zeros((T, E), np.uint8), obs=np.zeros((T, E, 2, cells), np.uint8))
+    L.o_batch_inject_steps(MAP[m], OBS[o], TARGET[t], lvl, E, 0, E, H, W, T, _p(maze), _p(pos0), _p(ctr0), _p(actions),
+                           _p(out["pos"]), _p(out["ctr"]), _p(out["rew"]), _p(out["done"]), _p(out["obs"]), _threads())
+    return out

@@ -689,3 +689,110 @@ long o_run_random(int map_type, int obs_type, int target_mode, int level, uint32
     o_destroy(e);
     return steps;
 }
+
+/* ------------------------------------------------------------------------------------------- */
+/* Batched replay for the full-size parity tests (pthreads: envs are independent).              */
+/*                                                                                              */
+/* o_batch_pipeline: env e of an E-wide batch behaves like the reference after                  */
+/* np.random.seed(seed0 + e): reset, then T steps with reset-on-done (the obs of a finished env */
+/* is replaced by its reset obs; rewards / done are the finishing step's -- what libtrack2d's   */
+/* T2D_FLAG_AUTO_RESET does).  One call handles envs [first, first + n); arrays are indexed     */
+/* [t][e] over the whole batch width E.  Any output pointer may be NULL.                        */
+/* o_batch_inject_steps: env e starts from an INJECTED (maze[e], pos0[e], ctr0[e]) and takes T  */
+/* steps without reset (no RNG involved for Adv / PZR / Far targets).                           */
+/* ------------------------------------------------------------------------------------------- */
+#include <pthread.h>
+
+typedef struct {
+    int map_type, obs_type, target_mode, level, T, H, W, inject;
+    long E, first, n;
+    uint32_t seed0;
+    const int *actions;
+    const uint8_t *maze0; const int *pos0, *ctr0;
+    uint8_t *reset_obs, *reset_maze; int *reset_pos;
+    int *pos, *ctr; double *rew; uint8_t *done; int *tgt_act; uint8_t *obs; uint32_t *rng_ckpt; int *plan_meta;
+    int tid, nthreads;
+    long n_done;
+} BatchJob;
+
+static void *batch_worker(void *arg) {
+    BatchJob *j = (BatchJob *)arg;
+    OEnv *e = o_create(j->map_type, j->obs_type, j->target_mode, j->level);
+    const size_t ob = (size_t)2 * (size_t)o_obs_cells(e);
+    uint8_t *scratch = (uint8_t *)malloc(2 * O_MAXCELLS);
+    for (long i = j->first + j->tid; i < j->first + j->n; i += j->nthreads) {
+        if (j->inject) {
+            o_set_state(e, j->H, j->W, j->maze0 + (size_t)i * (size_t)(j->H * j->W), j->pos0 + i * 4, j->ctr0[i * 2], j->ctr0[i * 2 + 1]);
+        } else {
+            o_seed(e, j->seed0 + (uint32_t)i);
+            o_reset(e, scratch);
+            if (j->reset_obs) memcpy(j->reset_obs + (size_t)i * ob, scratch, ob);
+            if (j->reset_maze) memcpy(j->reset_maze + (size_t)i * (size_t)(e->H * e->W), e->maze, (size_t)(e->H * e->W));
+            if (j->reset_pos) memcpy(j->reset_pos + i * 4, e->state, sizeof(e->state));
+        }
+        for (int t = 0; t < j->T; t++) {
+            const size_t k = (size_t)t * (size_t)j->E + (size_t)i;
+            double r[2];
+            int ta = 0;
+            int d = o_step(e, j->actions + k * 2, scratch, r, 0, &ta);
+            if (d && !j->inject) { o_reset(e, scratch); j->n_done++; }
+            if (j->pos) memcpy(j->pos + k * 4, e->state, sizeof(e->state));
+            if (j->ctr) { j->ctr[k * 2] = e->c_far; j->ctr[k * 2 + 1] = e->elapsed; }
+            if (j->rew) { j->rew[k * 2] = r[0]; j->rew[k * 2 + 1] = r[1]; }
+            if (j->done) j->done[k] = (uint8_t)d;
+            if (j->tgt_act) j->tgt_act[k] = ta;
+            if (j->obs) memcpy(j->obs + k * ob, scratch, ob);
+            if (j->plan_meta) {
+                int is_ram = e->target_mode == O_T_RAM;
+                j->plan_meta[k * 2] = is_ram ? e->ram_i : e->nav_i;
+                j->plan_meta[k * 2 + 1] = is_ram ? e->ram_len : e->nav_len;
+            }
+        }
+        if (j->rng_ckpt) {
+            memcpy(j->rng_ckpt + i * 9, e->rng.key, 8 * sizeof(uint32_t));
+            j->rng_ckpt[i * 9 + 8] = (uint32_t)e->rng.pos;
+        }
+    }
+    free(scratch);
+    o_destroy(e);
+    return 0;
+}
+
+static long batch_run(BatchJob *proto, int nthreads) {
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 64) nthreads = 64;
+    BatchJob jobs[64];
+    pthread_t th[64];
+    for (int t = 0; t < nthreads; t++) {
+        jobs[t] = *proto; jobs[t].tid = t; jobs[t].nthreads = nthreads; jobs[t].n_done = 0;
+        pthread_create(&th[t], 0, batch_worker, &jobs[t]);
+    }
+    long nd = 0;
+    for (int t = 0; t < nthreads; t++) { pthread_join(th[t], 0); nd += jobs[t].n_done; }
+    return nd;
+}
+
+long o_batch_pipeline(int map_type, int obs_type, int target_mode, int level, long E, long first, long n, uint32_t seed0, int T,
+                      const int *actions /*[T][E][2]*/, uint8_t *reset_obs /*[E][2][cells]*/, uint8_t *reset_maze /*[E][H][W]*/,
+                      int *reset_pos /*[E][4]*/, int *pos /*[T][E][4]*/, int *ctr /*[T][E][2]*/, double *rew /*[T][E][2]*/,
+                      uint8_t *done /*[T][E]*/, int *tgt_act /*[T][E]*/, uint8_t *obs /*[T][E][2][cells]*/, uint32_t *rng_ckpt /*[E][9]*/,
+                      int *plan_meta /*[T][E][2] = (idx, len) of the Navigator / RamAgent plan after the step*/, int nthreads) {
+    BatchJob j;
+    memset(&j, 0, sizeof(j));
+    j.map_type = map_type; j.obs_type = obs_type; j.target_mode = target_mode; j.level = level; j.T = T;
+    j.E = E; j.first = first; j.n = n; j.seed0 = seed0; j.actions = actions;
+    j.reset_obs = reset_obs; j.reset_maze = reset_maze; j.reset_pos = reset_pos;
+    j.pos = pos; j.ctr = ctr; j.rew = rew; j.done = done; j.tgt_act = tgt_act; j.obs = obs; j.rng_ckpt = rng_ckpt; j.plan_meta = plan_meta;
+    return batch_run(&j, nthreads);
+}
+
+void o_batch_inject_steps(int map_type, int obs_type, int target_mode, int level, long E, long first, long n, int H, int W, int T,
+                          const uint8_t *maze /*[E][H][W]*/, const int *pos0 /*[E][4]*/, const int *ctr0 /*[E][2]*/,
+                          const int *actions /*[T][E][2]*/, int *pos, int *ctr, double *rew, uint8_t *done, uint8_t *obs, int nthreads) {
+    BatchJob j;
+    memset(&j, 0, sizeof(j));
+    j.map_type = map_type; j.obs_type = obs_type; j.target_mode = target_mode; j.level = level; j.T = T; j.H = H; j.W = W; j.inject = 1;
+    j.E = E; j.first = first; j.n = n; j.actions = actions; j.maze0 = maze; j.pos0 = pos0; j.ctr0 = ctr0;
+    j.pos = pos; j.ctr = ctr; j.rew = rew; j.done = done; j.obs = obs;
+    batch_run(&j, nthreads);
+}

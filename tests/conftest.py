@@ -27,3 +27,22 @@ def golden_path(name):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+def pytest_collection_modifyitems(config, items):
+    """gpu-marked tests need a CUDA device AND the built library: skip them (instead of failing in cudaGetDevice) elsewhere"""
+    reason = None
+    try:
+        import torch
+        if not torch.cuda.is_available():
+            reason = "no CUDA device"
+    except Exception as ex:  # noqa: BLE001
+        reason = "torch unavailable: %r" % (ex,)
+    if reason is None and not os.path.exists(os.path.join(ROOT, "active_tracking_rl_b200", "libtrack2d.so")):
+        reason = "libtrack2d.so is not built"
+    if reason is None:
+        return
+    skip = pytest.mark.skip(reason=reason)
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
