@@ -69,6 +69,16 @@ SYMBOLS = {
     "track2d_get_counters": (C.c_int, [_vp, _vp, _vp]),
     "track2d_maze_conv_forward": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "track2d_maze_conv_backward": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "track2d_maze_conv_forward_ex": (C.c_int, [_vp, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "track2d_maze_conv_backward_ex": (C.c_int, [_vp, _i32, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "track2d_lstm_heads_forward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                             C.c_uint64, _u32, _i32, _i64, _vp]),
+    "track2d_policy_post_step": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "track2d_embed_add": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _i32, _i64, _vp]),
+    "track2d_a3c_loss_grad": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _dbl, _dbl, _dbl, _dbl, _dbl, _i32, _i32, _i32, _vp]),
+    "track2d_lstm_heads_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "track2d_relu_backward_workspace_floats": (C.c_int64, [_i64, _i32]),
+    "track2d_relu_backward_groupsum": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _i64, _vp]),
     "track2d_gae_returns": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i64, _dbl, _dbl, _vp]),
     "track2d_gemm_workspace_floats": (C.c_int64, [_i64, _i64, _i64]),
     "track2d_gemm_tf32x3": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _i32, _vp, _i64, _vp]),

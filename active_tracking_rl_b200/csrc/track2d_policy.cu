@@ -66,12 +66,14 @@ __device__ __forceinline__ void load_weights(ConvSmem &s, const float *__restric
     for (int i = tid; i < IMG * 16 * Y1P; i += THREADS) (&s.y1[0][0][0])[i] = 0.f;
 }
 
-// stage IMG images and run conv1 + ReLU into the zero-bordered y1 tile.  thread = (image, channel)
-__device__ __forceinline__ void stage_and_conv1(ConvSmem &s, const float *__restrict__ x, int64_t n0, int nimg, int tid) {
+// stage IMG images and run conv1 + ReLU into the zero-bordered y1 tile.  thread = (image, channel).  Images are float32 or
+// uint8 (the env's lossless observation encoding: cell values 0, 1, 2, 4), `xs` elements apart.
+template <typename XT>
+__device__ __forceinline__ void stage_and_conv1(ConvSmem &s, const XT *__restrict__ x, int64_t xs, int64_t n0, int nimg, int tid) {
     for (int i = tid; i < IMG * 169; i += THREADS) {
         int img = i / 169, c = i - img * 169;
         int r = c / 13, q = c - r * 13;
-        s.xs[img][(r + 1) * 15 + q + 1] = img < nimg ? x[(n0 + img) * 169 + c] : 0.f;
+        s.xs[img][(r + 1) * 15 + q + 1] = img < nimg ? (float)x[(n0 + img) * xs + c] : 0.f;
     }
     __syncthreads();
     const int img = tid >> 4, ch = tid & 15;
@@ -96,7 +98,8 @@ __device__ __forceinline__ void stage_and_conv1(ConvSmem &s, const float *__rest
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(THREADS) maze_conv_fwd_kernel(const float *__restrict__ x, int64_t N, const float *__restrict__ w1,
+template <typename XT>
+__global__ void __launch_bounds__(THREADS) maze_conv_fwd_kernel(const XT *__restrict__ x, int64_t xs, int64_t N, const float *__restrict__ w1,
                                                                 const float *__restrict__ b1, const float *__restrict__ w2,
                                                                 const float *__restrict__ b2, float *__restrict__ y2) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -111,7 +114,7 @@ __global__ void __launch_bounds__(THREADS) maze_conv_fwd_kernel(const float *__r
     const int oi = pp >> 1, oj0 = (pp & 1) * 2;
     for (int64_t n0 = (int64_t)blockIdx.x * IMG; n0 < N; n0 += (int64_t)gridDim.x * IMG) {
         const int nimg = (int)min((int64_t)IMG, N - n0);
-        stage_and_conv1(s, x, n0, nimg, tid);
+        stage_and_conv1(s, x, xs, n0, nimg, tid);
         float2 accA[8], accB[8];  // output-channel pairs
 #pragma unroll
         for (int c = 0; c < 8; c++) accA[c] = accB[c] = make_float2(s.b2[och * 16 + 2 * c], s.b2[och * 16 + 2 * c + 1]);
@@ -149,7 +152,8 @@ __global__ void __launch_bounds__(THREADS) maze_conv_fwd_kernel(const float *__r
     }
 }
 
-__global__ void __launch_bounds__(THREADS) maze_conv_bwd_kernel(const float *__restrict__ x, const float *__restrict__ y2,
+template <typename XT>
+__global__ void __launch_bounds__(THREADS) maze_conv_bwd_kernel(const XT *__restrict__ x, int64_t xs, const float *__restrict__ y2,
                                                                 const float *__restrict__ gy2, int64_t N, const float *__restrict__ w1,
                                                                 const float *__restrict__ b1, const float *__restrict__ w2,
                                                                 float *__restrict__ dw1, float *__restrict__ db1, float *__restrict__ dw2,
@@ -173,7 +177,7 @@ __global__ void __launch_bounds__(THREADS) maze_conv_bwd_kernel(const float *__r
 
     for (int64_t n0 = (int64_t)blockIdx.x * IMG; n0 < N; n0 += (int64_t)gridDim.x * IMG) {
         const int nimg = (int)min((int64_t)IMG, N - n0);
-        stage_and_conv1(s.f, x, n0, nimg, tid);
+        stage_and_conv1(s.f, x, xs, n0, nimg, tid);
         // dz2 = dL/dy2 * (y2 > 0), transposed to [img][pos][oc]
         {
             const int oc = tid & 31, q4 = tid >> 5; // 4 warps: each takes positions q4*4 .. q4*4+3
@@ -292,23 +296,45 @@ int grid_for(int64_t N, int ctas_per_sm) {
     return (int)(groups < g ? groups : g);
 }
 
+template <typename XT>
+cudaError_t conv_fwd_launch(const XT *x, int64_t xs, int64_t n, const float *w1, const float *b1, const float *w2, const float *b2, float *y2, cudaStream_t st) {
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_set[dev & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(maze_conv_fwd_kernel<XT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ConvSmem));
+        if (e != cudaSuccess) return e;
+        attr_set[dev & 63] = true;
+    }
+    maze_conv_fwd_kernel<XT><<<grid_for(n, 3), THREADS, sizeof(ConvSmem), st>>>(x, xs, n, w1, b1, w2, b2, y2);
+    return cudaGetLastError();
+}
+template <typename XT>
+cudaError_t conv_bwd_launch(const XT *x, int64_t xs, const float *y2, const float *gy2, int64_t n, const float *w1, const float *b1, const float *w2,
+                            float *dw1, float *db1, float *dw2, float *db2, cudaStream_t st) {
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_set[dev & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(maze_conv_bwd_kernel<XT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ConvBwdSmem));
+        if (e != cudaSuccess) return e;
+        attr_set[dev & 63] = true;
+    }
+    maze_conv_bwd_kernel<XT><<<grid_for(n, 2), THREADS, sizeof(ConvBwdSmem), st>>>(x, xs, y2, gy2, n, w1, b1, w2, dw1, db1, dw2, db2);
+    return cudaGetLastError();
+}
+
 } // namespace
 
-extern "C" int track2d_maze_conv_forward(const float *x, int64_t n_images, const float *w1, const float *b1, const float *w2,
-                                         const float *b2, float *y2, void *stream) {
-    if (!x || !w1 || !b1 || !w2 || !b2 || !y2 || n_images < 1) {
+extern "C" int track2d_maze_conv_forward_ex(const void *x, int32_t x_is_u8, int64_t x_stride, int64_t n_images, const float *w1, const float *b1,
+                                            const float *w2, const float *b2, float *y2, void *stream) {
+    if (!x || !w1 || !b1 || !w2 || !b2 || !y2 || n_images < 1 || x_stride < 169) {
         t2d_set_error("track2d_maze_conv_forward: bad argument");
         return T2D_E_INVALID;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(maze_conv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ConvSmem));
-        cudaFuncSetAttribute(maze_conv_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ConvBwdSmem));
-        attr_set = true;
-    }
     t2d_count_launches(1);
-    maze_conv_fwd_kernel<<<grid_for(n_images, 3), THREADS, sizeof(ConvSmem), (cudaStream_t)stream>>>(x, n_images, w1, b1, w2, b2, y2);
-    cudaError_t err = cudaGetLastError();
+    cudaError_t err = x_is_u8 ? conv_fwd_launch((const uint8_t *)x, x_stride, n_images, w1, b1, w2, b2, y2, (cudaStream_t)stream)
+                              : conv_fwd_launch((const float *)x, x_stride, n_images, w1, b1, w2, b2, y2, (cudaStream_t)stream);
     if (err != cudaSuccess) {
         t2d_set_error("track2d_maze_conv_forward: %s", cudaGetErrorString(err));
         return T2D_E_CUDA;
@@ -316,25 +342,29 @@ extern "C" int track2d_maze_conv_forward(const float *x, int64_t n_images, const
     return T2D_OK;
 }
 
-extern "C" int track2d_maze_conv_backward(const float *x, const float *y2, const float *gy2, int64_t n_images, const float *w1,
-                                          const float *b1, const float *w2, float *dw1, float *db1, float *dw2, float *db2, void *stream) {
-    if (!x || !y2 || !gy2 || !w1 || !b1 || !w2 || !dw1 || !db1 || !dw2 || !db2 || n_images < 1) {
+extern "C" int track2d_maze_conv_backward_ex(const void *x, int32_t x_is_u8, int64_t x_stride, const float *y2, const float *gy2, int64_t n_images,
+                                             const float *w1, const float *b1, const float *w2, float *dw1, float *db1, float *dw2, float *db2,
+                                             void *stream) {
+    if (!x || !y2 || !gy2 || !w1 || !b1 || !w2 || !dw1 || !db1 || !dw2 || !db2 || n_images < 1 || x_stride < 169) {
         t2d_set_error("track2d_maze_conv_backward: bad argument");
         return T2D_E_INVALID;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(maze_conv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ConvSmem));
-        cudaFuncSetAttribute(maze_conv_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ConvBwdSmem));
-        attr_set = true;
-    }
     t2d_count_launches(1);
-    maze_conv_bwd_kernel<<<grid_for(n_images, 2), THREADS, sizeof(ConvBwdSmem), (cudaStream_t)stream>>>(x, y2, gy2, n_images, w1, b1, w2, dw1, db1,
-                                                                                                        dw2, db2);
-    cudaError_t err = cudaGetLastError();
+    cudaError_t err = x_is_u8 ? conv_bwd_launch((const uint8_t *)x, x_stride, y2, gy2, n_images, w1, b1, w2, dw1, db1, dw2, db2, (cudaStream_t)stream)
+                              : conv_bwd_launch((const float *)x, x_stride, y2, gy2, n_images, w1, b1, w2, dw1, db1, dw2, db2, (cudaStream_t)stream);
     if (err != cudaSuccess) {
         t2d_set_error("track2d_maze_conv_backward: %s", cudaGetErrorString(err));
         return T2D_E_CUDA;
     }
     return T2D_OK;
+}
+
+extern "C" int track2d_maze_conv_forward(const float *x, int64_t n_images, const float *w1, const float *b1, const float *w2, const float *b2, float *y2,
+                                         void *stream) {
+    return track2d_maze_conv_forward_ex(x, 0, 169, n_images, w1, b1, w2, b2, y2, stream);
+}
+
+extern "C" int track2d_maze_conv_backward(const float *x, const float *y2, const float *gy2, int64_t n_images, const float *w1, const float *b1,
+                                          const float *w2, float *dw1, float *db1, float *dw2, float *db2, void *stream) {
+    return track2d_maze_conv_backward_ex(x, 0, 169, y2, gy2, n_images, w1, b1, w2, dw1, db1, dw2, db2, stream);
 }

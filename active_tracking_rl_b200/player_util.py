@@ -12,7 +12,7 @@ import ctypes as C
 
 import torch
 
-from . import _lib
+from . import _lib, learner
 
 
 class Agent(object):
@@ -45,6 +45,12 @@ class Agent(object):
         self._w_ent_key = (float(args.entropy), float(self.w_entropy_target))
         self.w_ent = torch.tensor(list(self._w_ent_key), device=self.device)
         self.lib = _lib.load() if self.device.type == 'cuda' else None
+        # the hand-written forward / backward (learner.FusedA3C) for the configurations it covers; the autograd path of model.py
+        # otherwise (CPU tensors, single-agent, stacked frames, Full observations)
+        self.engine = None
+        if self.device.type == 'cuda' and getattr(args, 'fused', True) and learner.supported(model, env, args):
+            self.engine = learner.FusedA3C(model, self.num_envs, int(args.num_steps), self.device, seed=int(getattr(args, 'seed', 1)) + 7919 * max(self.gpu_id, 0))
+            self.eps_len = self.engine.eps_len
         self._alloc_rollout()
         self.clear_actions()
 
@@ -53,7 +59,12 @@ class Agent(object):
         T, E = int(self.args.num_steps), self.num_envs
         obs_shape = tuple(self.env.obs.shape[1:])
         # the env writes straight into these (no copies): obs_buf[t + 1] <- step t
-        self.obs_buf = torch.zeros((T + 1, E) + obs_shape, dtype=torch.float32, device=self.device)
+        if self.engine is not None:
+            self.obs_buf = self.engine.obs  # uint8: the env's lossless observation encoding (values 0, 1, 2, 4)
+        else:
+            if E % 2:  # the step kernel stores 16-byte vectors: a float32 slot (E x 1,352 bytes) must keep that alignment
+                raise _lib.Track2DError("num_envs must be even for device-resident rollouts (16-byte aligned observation slots)")
+            self.obs_buf = torch.zeros((T + 1, E) + obs_shape, dtype=torch.float32, device=self.device)
         self.rew_buf = torch.zeros((T, E, 2), dtype=torch.float32, device=self.device)
         self.done_buf = torch.zeros((T, E), dtype=torch.uint8, device=self.device)
         self.val_buf = torch.zeros((T + 1, E, 2), dtype=torch.float32, device=self.device)
@@ -80,9 +91,13 @@ class Agent(object):
         self.hx_store.zero_()
         self.cx_store.zero_()
         self.hxs, self.cxs = self.hx_store, self.cx_store
+        if self.engine is not None:
+            self.engine.reset_state()
 
     def update_rnn_hiden(self):
         """truncate BPTT at the rollout boundary (player_util.py:104-106)"""
+        if self.engine is not None:  # the fused path keeps no graph: slot 0 already holds the state the rollout starts from
+            return
         if self.hxs is not self.hx_store:
             self.hx_store.copy_(self.hxs.detach())
             self.cx_store.copy_(self.cxs.detach())
@@ -97,6 +112,8 @@ class Agent(object):
         (player_util.py:54-59 `torch.from_numpy(state_multi).float().to(device)`)."""
         t = self.t
         assert t < self.rew_buf.shape[0], "rollout buffer full: call optimize()"
+        if self.engine is not None:
+            return self._action_train_fused(t, forced_actions, host)
         value, action, entropy, log_prob, (hxs, cxs), R_pred = self.model((self.state, (self.hxs, self.cxs)), False, forced_actions)
         actions32 = action.to(torch.int32).contiguous()
         if host is None:
@@ -131,8 +148,71 @@ class Agent(object):
         self.t = t + 1
         return self
 
+    def _action_train_fused(self, t, forced_actions, host):
+        eng = self.engine
+        if forced_actions is not None:
+            forced_actions = forced_actions.to(device=self.device, dtype=torch.int32).contiguous()
+        actions32 = eng.forward(t, forced=forced_actions)
+        if host is None:
+            self.env.step_into(actions32, self.obs_buf[t + 1], self.rew_buf[t], self.done_buf[t])
+        else:
+            host['actions'].copy_(actions32)  # D2H, synchronous
+            self.env.step_host(host['actions'], host['obs'], host['reward'], host['done'])
+            if host['obs'].dtype == torch.uint8:
+                self.obs_buf[t + 1].copy_(host['obs'], non_blocking=True)
+            else:  # float32 on the host side (the reference's dtype): upload, then narrow on the device (lossless: values 0, 1, 2, 4)
+                if getattr(self, '_obs_f32', None) is None:
+                    self._obs_f32 = torch.empty(host['obs'].shape, dtype=torch.float32, device=self.device)
+                self._obs_f32.copy_(host['obs'], non_blocking=True)
+                self.obs_buf[t + 1].copy_(self._obs_f32)
+            self.rew_buf[t].copy_(host['reward'], non_blocking=True)
+            self.done_buf[t].copy_(host['done'], non_blocking=True)
+        eng.post_step(t, self.done_buf[t])
+        self.reward = self.rew_buf[t]
+        self.done = self.done_buf[t]
+        self.state = self.obs_buf[t + 1]
+        self.n_steps += self.num_envs
+        self.last_actions = actions32
+        self.t = t + 1
+        return self
+
+    @property
+    def fused(self):
+        return self.engine is not None
+
+    # recurrent state as the reference exposes it, (E, 2, 128) each; with the fused engine: the state entering the current step
+    @property
+    def hxs(self):
+        return self.engine.hidden(self.t)[0] if self.engine is not None else self._hxs
+
+    @hxs.setter
+    def hxs(self, v):
+        self._hxs = v
+
+    @property
+    def cxs(self):
+        return self.engine.hidden(self.t)[1] if self.engine is not None else self._cxs
+
+    @cxs.setter
+    def cxs(self, v):
+        self._cxs = v
+
+    def _action_test_fused(self):
+        eng = self.engine
+        actions32 = eng.forward(0, greedy=True, bootstrap=True)
+        obs, reward, done = self.env.step(actions32)
+        self.reward, self.done = reward, done
+        self.obs_buf[0].copy_(obs)
+        eng.post_step(0, done)
+        eng.carry_over(1, obs=False)
+        self.state = self.obs_buf[0]
+        self.n_steps += self.num_envs
+        return self
+
     def action_test(self):
         """greedy step (player_util.py:69-82); used by the evaluator"""
+        if self.engine is not None:
+            return self._action_test_fused()
         with torch.no_grad():
             value, action, entropy, log_prob, (hxs, cxs), R_pred = self.model((self.state, (self.hxs, self.cxs)), True)
         actions32 = action.to(torch.int32).contiguous()
@@ -165,6 +245,8 @@ class Agent(object):
         `device_share` are accepted for call compatibility: the model IS the shared model here."""
         T, E = self.t, self.num_envs
         assert T > 0
+        if self.engine is not None:
+            return self._optimize_fused(T, optimizer, training_mode, world_size, allreduce, boot_forced_actions, apply)
         with torch.no_grad():  # player_util.py:110-116, value only matters where the episode is still running
             v_boot, _, _, _, _, _ = self.model((self.state, (self.hxs, self.cxs)), False, boot_forced_actions)
             self.val_buf[T].copy_(v_boot)
@@ -204,6 +286,20 @@ class Agent(object):
             self.apply_update(optimizer, world_size, allreduce)
         return self._stats
 
+    def _optimize_fused(self, T, optimizer, training_mode, world_size, allreduce, boot_forced_actions, apply):
+        eng = self.engine
+        if boot_forced_actions is not None:
+            boot_forced_actions = boot_forced_actions.to(device=self.device, dtype=torch.int32).contiguous()
+        eng.forward(T, forced=boot_forced_actions, bootstrap=True)  # player_util.py:110-116 (it samples, like the reference)
+        key = (float(self.args.entropy), float(self.w_entropy_target))
+        optimizer.zero_grad()
+        use_aux = 'reward' in self.args.aux
+        self._stats = eng.backward(T, self.rew_buf, self.done_buf, training_mode, key, use_aux, float(self.args.gamma), float(self.args.tau),
+                                   1.0 / self.num_envs)  # loss.mean() over envs == average of the per-worker gradients
+        if apply:
+            self.apply_update(optimizer, world_size, allreduce)
+        return self._stats
+
     def apply_update(self, optimizer, world_size=1, allreduce=None, skip_allreduce=False):
         """second half of optimize(): [all-reduce of the flat gradient], [clip] + SharedAdam, and the hand-over of observation /
         recurrent state to the next rollout.  Split off so that a multi-GPU run can replay the two halves as CUDA graphs with the
@@ -211,6 +307,13 @@ class Agent(object):
         if allreduce is not None and world_size > 1 and not skip_allreduce:
             allreduce(optimizer.fp.grad)
         optimizer.step(max_grad_norm=self.max_grad_norm, grad_scale=1.0 / world_size)
+        if self.engine is not None:
+            T = self.t
+            self.engine.mark_dirty()
+            self.engine.carry_over(T)
+            self.clear_actions()
+            self.state = self.obs_buf[0]
+            return self._stats
         self.clear_actions()
         self.obs_buf.data[0].copy_(self.state)
         self.state = self.obs_buf[0]

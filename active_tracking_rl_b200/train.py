@@ -54,6 +54,8 @@ def make_parser():
     p.add_argument('--max-grad-norm', type=float, default=0.0,
                    help='0 = the reference\'s effective behaviour (its clip_grad_norm_(params, 50) is inert); 50 = its intent')
     p.add_argument('--fp32-emulation', action='store_true', help='fp32 GEMMs through cuBLAS 12.9 BF16x9 emulation (see blas.py)')
+    p.add_argument('--no-fused', dest='fused', action='store_false',
+                   help='run the policy through model.py\'s autograd path instead of the hand-written forward / backward (learner.FusedA3C)')
     p.add_argument('--tf32', action='store_true', help='allow TF32 tensor-core math in the policy (off: float32 like the reference)')
     return p
 
@@ -92,6 +94,8 @@ class Trainer(object):
         self.player = Agent(self.model, self.env, args, None, self.device)
         self.player.w_entropy_target = args.entropy_target
         self.player.max_grad_norm = float(getattr(args, 'max_grad_norm', 0.0))
+        if self.player.engine is not None:  # train.py:20: every worker samples from its own stream
+            self.player.engine.seed = (int(args.seed) + 1000003 * rank) & 0xFFFFFFFFFFFFFFFF
         self.player.reset()
         self.n_iter = 0
         self.allreduce = None

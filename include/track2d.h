@@ -201,6 +201,15 @@ int track2d_maze_conv_backward(const float *x_dev, const float *y2_dev, const fl
                                const float *b1_dev, const float *w2_dev, float *dw1_dev, float *db1_dev, float *dw2_dev, float *db2_dev,
                                void *stream);
 
+/* the same two kernels with the image source made explicit: x is float32 (x_is_u8 == 0) or uint8 (the env's lossless observation
+ * encoding, cell values 0, 1, 2, 4: track2d_step_u8), consecutive images x_stride ELEMENTS apart (169 = packed; 338 = one agent's
+ * image out of an [E][2][13][13] observation buffer). */
+int track2d_maze_conv_forward_ex(const void *x_dev, int32_t x_is_u8, int64_t x_stride, int64_t n_images, const float *w1_dev, const float *b1_dev,
+                                 const float *w2_dev, const float *b2_dev, float *y2_dev, void *stream);
+int track2d_maze_conv_backward_ex(const void *x_dev, int32_t x_is_u8, int64_t x_stride, const float *y2_dev, const float *gy2_dev, int64_t n_images,
+                                  const float *w1_dev, const float *b1_dev, const float *w2_dev, float *dw1_dev, float *db1_dev, float *dw2_dev,
+                                  float *db2_dev, void *stream);
+
 /* float32-accurate GEMM on the tcgen05 tensor cores (3xTF32 split, fp32 accumulation in TMEM) for the policy's Linear /
  * LSTMCell layers (reference: nn.Linear / nn.LSTMCell in model.py:116-127,175-182, perception.py:73 -- fp32 on the CPU):
  *     D[m][n] = act( sum_k A(m,k) * B(n,k) + bias[n] ),  m < M, n < N, k < K;  D row-major with leading dimension ldd.
@@ -234,6 +243,55 @@ int track2d_lstm_cell_backward(const float *dhy_dev, int64_t dhy_stride, const f
 int64_t track2d_colsum_workspace_floats(int64_t M, int32_t N);
 int track2d_colsum(const float *x_dev, int64_t ld, int64_t M, int32_t N, float *out_dev, float *workspace_dev, int64_t workspace_floats,
                    void *stream);
+
+/* ---- the recurrent half of the policy step and the A3C loss, fused (csrc/track2d_a3c.cu) ------------------------------------
+ * Reference: model.py:41-50 (sample_action), :116-127 / :175-209 (LSTMCell + actor / critic / reward_aux heads),
+ * player_util.py:108-161 (Agent.optimize).  Hidden size 128.  "Packed heads" = an [8][128] weight / [8] bias / [E][8] output
+ * whose rows are: 4 actor logits, the critic value, the TAT's reward prediction (or 0), 2 x padding.  All pointers are device
+ * pointers, 16-byte aligned unless they address single columns. */
+
+/* One policy step after the gate GEMM (gates_dev [E][512] = [feature | h] [W_ih | W_hh]^T, no bias): LSTM cell -> packed heads ->
+ * softmax / log-softmax / entropy -> action.  Writes act_dev [E][512] (activated gates, for the backward; may be NULL), c_next_dev
+ * [E][128], h_out_dev [E][128] (may be NULL), the same h into h_next_dev rows of stride h_next_ld floats (the recurrent input slot
+ * of the next step's GEMM; may be NULL), out8_dev [E][8] (may be NULL).  action_dev / forced_dev / value_dev / logp_dev /
+ * entropy_dev address ONE COLUMN of [E][2] arrays (element stride 2).  The action is forced_dev's when given, the argmax when
+ * `greedy` (player_util.py:69-82 action_test; logp_all_dev [E][4] then receives the log-probabilities, model.py:45-46), otherwise
+ * a multinomial sample drawn with Philox4x32-10 keyed by `seed` at counter (row, rng_stream, *rng_step_dev). */
+int track2d_lstm_heads_forward(const float *gates_dev, const float *b_ih_dev, const float *b_hh_dev, const float *c_prev_dev, float *act_dev,
+                               float *c_next_dev, float *h_out_dev, float *h_next_dev, int64_t h_next_ld, const float *w_head_dev,
+                               const float *b_head_dev, float *out8_dev, int32_t *action_dev, const int32_t *forced_dev, float *value_dev,
+                               float *logp_dev, float *entropy_dev, float *logp_all_dev, const uint64_t *rng_step_dev, uint64_t seed,
+                               uint32_t rng_stream, int32_t greedy, int64_t E, void *stream);
+/* After env.step: envs whose done byte is set start the next step from zero recurrent state (train.py:73-74 -> Agent.reset):
+ * zeroes their rows of h0 / h1 (row stride h_ld) and c0 / c1 ([E][128]); eps_len += 1 or = 0 (player_util.py:63,101); advances
+ * the sampling counter.  Any pointer may be NULL. */
+int track2d_policy_post_step(const uint8_t *done_dev, float *h0_dev, float *h1_dev, int64_t h_ld, float *c0_dev, float *c1_dev,
+                             int32_t *eps_len_dev, uint64_t *rng_step_dev, int64_t E, void *stream);
+/* out[e][j] = x[e][j] + w[j][action[e]] + b[j], j < N: TAT's fc_action_tracker applied to the one-hot tracker action
+ * (model.py:198-199); w [N][4]; row strides ld / out_ld floats; action_dev = one column of an int32 [E][2] array. */
+int track2d_embed_add(const float *x_dev, int64_t ld, float *out_dev, int64_t out_ld, const float *w_dev, const float *b_dev,
+                      const int32_t *action_dev, int32_t N, int64_t E, void *stream);
+/* Agent.optimize's recursions and loss gradients for all envs (player_util.py:117-145): from the packed head outputs of both
+ * agents (out8_*_dev [T+1][E][8], slot T = the bootstrap forward), actions [T][E][2], rewards [T][E][2], done [T][E]:
+ * n-step returns and GAE cut at episode ends, then dL/d(out8) -> dout8_*_dev [T][E][8] for L = scale * sum_e sum_t of the
+ * reference's per-step loss terms of the agents with train_k != 0 (+ the aux L1 when use_aux), and the per-env statistics
+ * stats_dev [7][E] = policy_loss 0/1, value_loss 0/1, entropy 0/1, pred_loss.  returns_dev / gae_dev [T][E][2] optional. */
+int track2d_a3c_loss_grad(const float *out8_0_dev, const float *out8_1_dev, float *dout8_0_dev, float *dout8_1_dev, const int32_t *actions_dev,
+                          const float *rewards_dev, const uint8_t *done_dev, float *stats_dev, float *returns_dev, float *gae_dev, int32_t T,
+                          int64_t E, double gamma, double tau, double w_ent0, double w_ent1, double scale, int32_t train0, int32_t train1,
+                          int32_t use_aux, void *stream);
+/* Backward of track2d_lstm_heads_forward for one step of the BPTT sweep: dgates_dev [E][512] from dout8_dev [E][8] (through the
+ * packed head weights) plus, when dh_rec_dev != NULL, the recurrent gradients dh_rec_dev [E][128] / dc_dev [E][128] of step t+1,
+ * both dropped where done_dev[e] (the episode ended at this step).  dc_dev is overwritten with dL/dc_prev. */
+int track2d_lstm_heads_backward(const float *dout8_dev, const float *w_head_dev, const float *dh_rec_dev, float *dc_dev, const uint8_t *done_dev,
+                                const float *act_dev, const float *c_prev_dev, float *dgates_dev, int64_t E, void *stream);
+/* In place dy *= (y > 0) over [M][N] (y rows y_ld floats apart; ReLU backward of the encoder fc, perception.py:91) and, in the same pass, dbias = column sums
+ * of the result; with group_dev (one column of an int32 [M][2] array, values 0..3) also the gradients of a Linear(4, N) whose
+ * one-hot-selected output was added after the ReLU: gw_dev [N][4] = per-group column sums of the incoming dy, gb_dev [N] = their
+ * total.  Fixed summation order; workspace of track2d_relu_backward_workspace_floats(M, N) floats. */
+int64_t track2d_relu_backward_workspace_floats(int64_t M, int32_t N);
+int track2d_relu_backward_groupsum(float *dy_dev, const float *y_dev, int64_t y_ld, const int32_t *group_dev, int64_t M, int32_t N,
+                                   float *dbias_dev, float *gw_dev, float *gb_dev, float *workspace_dev, int64_t workspace_floats, void *stream);
 
 #ifdef __cplusplus
 }
