@@ -113,6 +113,29 @@ def load():
     return lib
 
 
+class on_device(object):
+    """The learner kernels (GEMM, conv stack, LSTM, A3C loss, SharedAdam) launch on the CURRENT CUDA device with a stream of the
+    operands' device: make that device current for the duration of the call (no-op when it already is)."""
+
+    def __init__(self, device):
+        self.idx = device.index if device.index is not None else 0
+        self.prev = None
+
+    def __enter__(self):
+        import torch
+        cur = torch.cuda.current_device()
+        if cur != self.idx:
+            self.prev = cur
+            torch.cuda.set_device(self.idx)
+        return self
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            import torch
+            torch.cuda.set_device(self.prev)
+        return False
+
+
 def check(rc, lib=None):
     if rc != 0:
         lib = lib or load()

@@ -201,7 +201,7 @@ struct LossArgs {
     long long E;
     float gamma, tau, w_ent[2], scale;
     int train[2];            // agent's loss is part of the objective (training_mode -1 / 0 / 1)
-    int use_aux;             // reward_aux L1 term is part of the objective
+    int use_aux;             // reward_aux L1 term: 0 = the net has no such head, 1 = statistic only, 2 = part of the objective
 };
 
 // thread = (env, agent), t = T-1 .. 0.  player_util.py:117-145.
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(256) a3c_loss_grad_kernel(const LossArgs a) {
     float R = o8[((long long)a.T * a.E + e) * NOUT + 4], vnext = R, gae = 0.f;
     float pl = 0.f, vl = 0.f, ent = 0.f, prl = 0.f;
     const float w = a.w_ent[ag], sc = a.train[ag] ? a.scale : 0.f;
-    const float sc_aux = (ag == 1 && a.use_aux) ? a.scale : 0.f;
+    const float sc_aux = (ag == 1 && a.use_aux == 2) ? a.scale : 0.f;
     for (int t = a.T - 1; t >= 0; --t) {
         const long long k = (long long)t * a.E + e;
         const float4 z = ld4(o8 + k * NOUT), vp = ld4(o8 + k * NOUT + 4);
@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(256) a3c_loss_grad_kernel(const LossArgs a) {
         dz.z = sc * (-gae * ((act == 2 ? 1.f : 0.f) - p2) + w * p2 * (l2 + Hn));
         dz.w = sc * (-gae * ((act == 3 ? 1.f : 0.f) - p3) + w * p3 * (l3 + Hn));
         float dpred = 0.f;
-        if (ag == 1) {                   // L1 between the target's prediction and the TRACKER's reward (:128-129)
+        if (ag == 1 && a.use_aux) {      // L1 between the target's prediction and the TRACKER's reward (:128-129)
             const float diff = pred - a.rewards[k * 2];
             prl += fabsf(diff);
             dpred = sc_aux * (diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f));

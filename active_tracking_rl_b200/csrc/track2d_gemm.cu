@@ -460,15 +460,19 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float *__restr
     }
 }
 
-int g_sm_count = 0;
+// per-device caches: the kernels launch on the CURRENT device (the Python side makes the operands' device current)
+constexpr int MAX_DEVICES = 64;
+int g_sm_counts[MAX_DEVICES] = {};
 
 template <bool A_MN, bool B_MN, int SM, int SN>
 cudaError_t launch(const GemmParams &p, int grid, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[MAX_DEVICES] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured[dev % MAX_DEVICES]) {
         cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel<A_MN, B_MN, SM, SN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured[dev % MAX_DEVICES] = true;
     }
     gemm_tf32x3_kernel<A_MN, B_MN, SM, SN><<<grid, THREADS, SMEM_BYTES, st>>>(p);
     return cudaGetLastError();
@@ -524,9 +528,14 @@ extern "C" int track2d_gemm_tf32x3(const float *a_dev, int a_mn_major, int64_t l
         return T2D_E_INVALID;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        t2d_set_error("track2d_gemm_tf32x3: cannot query the device");
+        return T2D_E_CUDA;
+    }
+    int &g_sm_count = g_sm_counts[dev % MAX_DEVICES];
     if (g_sm_count == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || g_sm_count <= 0) {
+        if (cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || g_sm_count <= 0) {
             t2d_set_error("track2d_gemm_tf32x3: cannot query the device");
             g_sm_count = 0;
             return T2D_E_CUDA;

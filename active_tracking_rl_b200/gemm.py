@@ -47,8 +47,9 @@ def gemm(a, a_mn_major, lda, b, b_mn_major, ldb, M, N, K, bias=None, relu=False,
     if out is None:
         out = torch.empty((M, N), dtype=torch.float32, device=dev)
     ws, n_ws = _workspace(lib, M, N, K, dev)
-    _lib.check(lib.track2d_gemm_tf32x3(_p(a), int(a_mn_major), lda, _p(b), int(b_mn_major), ldb, _p(out), out.stride(0), M, N, K,
-                                       _p(bias), int(relu), _p(ws), n_ws, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), lib)
+    with _lib.on_device(dev):
+        _lib.check(lib.track2d_gemm_tf32x3(_p(a), int(a_mn_major), lda, _p(b), int(b_mn_major), ldb, _p(out), out.stride(0), M, N, K,
+                                           _p(bias), int(relu), _p(ws), n_ws, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), lib)
     return out
 
 
@@ -72,7 +73,8 @@ def colsum(x):
     if ws is None:
         ws = _WS[key] = torch.empty(int(lib.track2d_colsum_workspace_floats(M, N)), dtype=torch.float32, device=x.device)
     out = torch.empty(N, dtype=torch.float32, device=x.device)
-    _lib.check(lib.track2d_colsum(_p(x), x.stride(0), M, N, _p(out), _p(ws), ws.numel(), C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)), lib)
+    with _lib.on_device(x.device):
+        _lib.check(lib.track2d_colsum(_p(x), x.stride(0), M, N, _p(out), _p(ws), ws.numel(), C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)), lib)
     return out
 
 
@@ -126,8 +128,9 @@ class _LSTMCellPointwise(torch.autograd.Function):
         hy = torch.empty((E, H), dtype=torch.float32, device=dev)
         cy = torch.empty((E, H), dtype=torch.float32, device=dev)
         act = torch.empty((E, H4), dtype=torch.float32, device=dev)
-        _lib.check(lib.track2d_lstm_cell_forward(_p(igates), _p(hgates), _p(b_ih), _p(b_hh), _p(cx), cx.stride(0), _p(hy), _p(cy), _p(act), E, H,
-                                                 C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), lib)
+        with _lib.on_device(dev):
+            _lib.check(lib.track2d_lstm_cell_forward(_p(igates), _p(hgates), _p(b_ih), _p(b_hh), _p(cx), cx.stride(0), _p(hy), _p(cy), _p(act), E, H,
+                                                     C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), lib)
         ctx.save_for_backward(cx, cy, act)
         ctx.set_materialize_grads(False)
         return hy, cy
@@ -151,9 +154,10 @@ class _LSTMCellPointwise(torch.autograd.Function):
         ws = _WS.get(key)
         if ws is None:
             ws = _WS[key] = torch.empty(n_ws, dtype=torch.float32, device=dev)
-        _lib.check(lib.track2d_lstm_cell_backward(_p(dhy), dhy.stride(0) if dhy is not None else H, _p(dcy), dcy.stride(0) if dcy is not None else H,
-                                                  _p(cx), cx.stride(0), _p(cy), _p(act), _p(dgates), _p(dcx), _p(db), _p(ws), n_ws, E, H,
-                                                  C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), lib)
+        with _lib.on_device(dev):
+            _lib.check(lib.track2d_lstm_cell_backward(_p(dhy), dhy.stride(0) if dhy is not None else H, _p(dcy), dcy.stride(0) if dcy is not None else H,
+                                                      _p(cx), cx.stride(0), _p(cy), _p(act), _p(dgates), _p(dcx), _p(db), _p(ws), n_ws, E, H,
+                                                      C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), lib)
         return dgates, dgates, dcx, db, db
 
 

@@ -121,6 +121,7 @@ def main():
     p.add_argument('--rnn-out', type=int, default=128)
     a = p.parse_args()
     device = torch.device('cuda:%d' % max(a.gpu_id, 0))
+    torch.cuda.set_device(device)
     args = default_args(network=a.network, stack_frames=a.stack_frames, rnn_out=a.rnn_out, seed=a.seed)
     torch.manual_seed(a.seed)
     probe = Track2DVecEnv(a.env, num_envs=1, device=device, seed=a.seed)

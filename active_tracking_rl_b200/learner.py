@@ -167,6 +167,10 @@ class FusedA3C(object):
         """policy step `t` from self.obs[t] and the recurrent state in slot t: fills actions[t], values[t], logp[t],
         entropy[t] and the state of slot t + 1.  `bootstrap`: the value-only forward of Agent.optimize (player_util.py:110-116;
         it still samples, as the reference does) -- nothing is kept for the backward."""
+        with _lib.on_device(self.device):
+            return self._forward(t, forced, greedy, bootstrap)
+
+    def _forward(self, t, forced, greedy, bootstrap):
         lib, E, st = self.lib, self.E, self._stream()
         if self._dirty:
             self.pack()
@@ -203,8 +207,9 @@ class FusedA3C(object):
     def post_step(self, t, done):
         """after env.step of step t: zero the recurrent state of finished envs in slot t + 1, eps_len, sampling counter"""
         n0, n1 = self.nets
-        _lib.check(self.lib.track2d_policy_post_step(_p(done), C.c_void_p(n0.xh[t + 1].data_ptr() + 4 * 256), C.c_void_p(n1.xh[t + 1].data_ptr() + 4 * 256),
-                                                     384, _p(n0.c[t + 1]), _p(n1.c[t + 1]), _p(self.eps_len), _p(self.rng_step), self.E, self._stream()), self.lib)
+        with _lib.on_device(self.device):
+            _lib.check(self.lib.track2d_policy_post_step(_p(done), C.c_void_p(n0.xh[t + 1].data_ptr() + 4 * 256), C.c_void_p(n1.xh[t + 1].data_ptr() + 4 * 256),
+                                                         384, _p(n0.c[t + 1]), _p(n1.c[t + 1]), _p(self.eps_len), _p(self.rng_step), self.E, self._stream()), self.lib)
 
     @torch.no_grad()
     def carry_over(self, T, obs=True):
@@ -221,6 +226,10 @@ class FusedA3C(object):
         """Fills p.grad of the trained agents' parameters with the gradient of
         scale * sum_e [loss_tracker + loss_target (+ pred_loss)] (player_util.py:141-155) and returns the per-env statistics
         (policy_loss (E,2), value_loss (E,2), entropy sums (E,2), pred_loss (E,)).  Needs forward(T, bootstrap=True) first."""
+        with _lib.on_device(self.device):
+            return self._backward(T, rewards, done, training_mode, w_ent, use_aux, gamma, tau, scale)
+
+    def _backward(self, T, rewards, done, training_mode, w_ent, use_aux, gamma, tau, scale):
         lib, E, st = self.lib, self.E, self._stream()
         M2 = T * E
         train = [training_mode in (-1, 0) and self.nets[0].trainable(), training_mode in (-1, 1) and self.nets[1].trainable()]
@@ -230,7 +239,7 @@ class FusedA3C(object):
         n0, n1 = self.nets
         _lib.check(lib.track2d_a3c_loss_grad(_p(n0.out8), _p(n1.out8), _p(n0.dout8), _p(n1.dout8), _p(self.actions), _p(rewards), _p(done), _p(self.stats),
                                              _p(self.returns), _p(self.gae), T, E, float(gamma), float(tau), float(w_ent[0]), float(w_ent[1]), float(scale),
-                                             int(train[0]), int(train[1]), int(aux), st), lib)
+                                             int(train[0]), int(train[1]), 2 if aux else int(bool(use_aux) and self.nets[1].tat), st), lib)
         for n in self.nets:
             if not (train[n.agent] or (n.agent == 1 and aux)):
                 continue

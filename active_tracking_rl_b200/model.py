@@ -74,8 +74,9 @@ class _MazeConvStack(torch.autograd.Function):
         N = x.shape[0]
         y2 = torch.empty((N, 512), dtype=torch.float32, device=x.device)
         p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
-        _lib.check(lib.track2d_maze_conv_forward(p(x), N, p(w1), p(b1), p(w2), p(b2), p(y2),
-                                                 C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)), lib)
+        with _lib.on_device(x.device):
+            _lib.check(lib.track2d_maze_conv_forward(p(x), N, p(w1), p(b1), p(w2), p(b2), p(y2),
+                                                     C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)), lib)
         ctx.save_for_backward(x, y2, w1, b1, w2)
         return y2
 
@@ -89,8 +90,9 @@ class _MazeConvStack(torch.autograd.Function):
         dw1, db1, dw2 = torch.zeros_like(w1), torch.zeros_like(b1), torch.zeros_like(w2)
         db2 = torch.zeros(32, dtype=torch.float32, device=x.device)
         p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
-        _lib.check(lib.track2d_maze_conv_backward(p(x), p(y2), p(gy2), x.shape[0], p(w1), p(b1), p(w2), p(dw1), p(db1), p(dw2), p(db2),
-                                                  C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)), lib)
+        with _lib.on_device(x.device):
+            _lib.check(lib.track2d_maze_conv_backward(p(x), p(y2), p(gy2), x.shape[0], p(w1), p(b1), p(w2), p(dw1), p(db1), p(dw2), p(db2),
+                                                      C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)), lib)
         return None, dw1, db1, dw2, db2
 
 

@@ -47,7 +47,12 @@ class FlatParams(object):
 
 class SharedAdam(object):
     """AMSGrad with eps added after the square root and bias correction folded into the step size
-    (shared_optim.py:155-173), fused with clip_grad_norm_ (player_util.py:157)."""
+    (shared_optim.py:155-173), fused with clip_grad_norm_ (player_util.py:157).
+
+    One update counter for the whole flat buffer (the reference keeps state['step'] per parameter and skips parameters whose
+    grad is None).  The two agree whenever every parameter of the optimizer gets a gradient in every update -- all README
+    commands.  With --init-step > 0 (tracker-only phase while the optimizer holds both agents) the target's moments decay and
+    its bias-correction step runs ahead during that phase; its weights do not move (zero gradient, zero first moment)."""
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-3, weight_decay=0, amsgrad=True):
         if weight_decay != 0 or not amsgrad:
@@ -73,10 +78,11 @@ class SharedAdam(object):
         self.step_count += 1
         dev = self.fp.flat.device
         p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
-        _lib.check(self.lib.track2d_sharedadam_step(
-            p(self.fp.flat), p(self.fp.grad), p(self.exp_avg), p(self.exp_avg_sq), p(self.max_exp_avg_sq), self.fp.numel,
-            self.step_count, self.lr, self.betas[0], self.betas[1], self.eps, float(max_grad_norm or 0.0), float(grad_scale),
-            p(self.norm_scratch), p(self.step_dev), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), self.lib)
+        with _lib.on_device(dev):
+            _lib.check(self.lib.track2d_sharedadam_step(
+                p(self.fp.flat), p(self.fp.grad), p(self.exp_avg), p(self.exp_avg_sq), p(self.max_exp_avg_sq), self.fp.numel,
+                self.step_count, self.lr, self.betas[0], self.betas[1], self.eps, float(max_grad_norm or 0.0), float(grad_scale),
+                p(self.norm_scratch), p(self.step_dev), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), self.lib)
 
     def advance_for_replay(self):
         """a CUDA-graph replay of step() advances the device counter by itself; keep the host mirror in sync"""

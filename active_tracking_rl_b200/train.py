@@ -50,7 +50,10 @@ def make_parser():
     p.add_argument('--init-step', type=int, default=-1)
     # batched-run additions
     p.add_argument('--num-envs', type=int, default=4096, help='envs per GPU')
-    p.add_argument('--iters', type=int, default=100, help='rollout+update iterations to run')
+    p.add_argument('--iters', type=int, default=100, help='rollout+update iterations to run (the run also stops once --max-step updates are done)')
+    p.add_argument('--eval-every', type=int, default=0,
+                   help='evaluate + checkpoint every this many updates on rank 0 (test.py:56-134); 0 = only once, at the end')
+    p.add_argument('--graph', action='store_true', help='replay each iteration from a CUDA graph (Trainer.capture)')
     p.add_argument('--max-grad-norm', type=float, default=0.0,
                    help='0 = the reference\'s effective behaviour (its clip_grad_norm_(params, 50) is inert); 50 = its intent')
     p.add_argument('--fp32-emulation', action='store_true', help='fp32 GEMMs through cuBLAS 12.9 BF16x9 emulation (see blas.py)')
@@ -174,7 +177,18 @@ class Trainer(object):
         torch.save(self.model.state_dict(), path)
 
 
+def scheduled_mode(args, n_iter):
+    """test.py:84-91: until `init_step` updates only the tracker learns (mode 0), afterwards --train-mode"""
+    return 0 if n_iter < args.init_step else args.train_mode
+
+
 def main():
+    """main.py:54-116 + test.py:56-134 for the synchronous learner: train, evaluate on --env-base every --eval-every updates, keep
+    the best tracker (all-best-{n}.dat / all-new.dat and, with --split, tracker-/target-{best,new}.dat under --log-dir/<env>/<date>),
+    follow the init_step training-mode schedule, stop after --max-step updates or --iters iterations.  An "update" here is one
+    optimizer step on the mean gradient of num_envs x num_steps env-steps (n_iter of the reference counts optimize() calls too)."""
+    from datetime import datetime
+    from .gym_eval import Evaluator
     args = make_parser().parse_args()
     if args.fp32_emulation and not blas.status()["enabled"]:
         print("note: --fp32-emulation needs `blas.enable_fp32_emulation()` before torch is imported; run through "
@@ -184,18 +198,45 @@ def main():
     rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
     torch.cuda.set_device(local_rank)
+    dev = 'cuda:%d' % local_rank
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group('nccl')
-    tr = Trainer(args, 'cuda:%d' % local_rank, rank, world)
+        dist.init_process_group('nccl', device_id=torch.device(dev))
+    tr = Trainer(args, dev, rank, world)
+    ev = None
+    if rank == 0:
+        log_dir = os.path.join(args.log_dir, args.env, datetime.now().strftime('%b%d_%H-%M'))  # main.py:97-98
+        ev = Evaluator(args, log_dir, dev)
+
+    def evaluate():
+        if ev is None:
+            return None
+        st = ev.run(tr.model, tr.n_iter)
+        print('eval @ %d updates (%s, %d episodes): R_mean %.3f  EL_mean %.1f  S_rate %.3f  -> %s' % (
+            tr.n_iter, st['Env'], st['episodes'], st['R_mean'], st['EL_mean'], st['S_rate'], os.path.join(ev.log_dir, st['checkpoint'])), flush=True)
+        return st
+
     t0 = time.time()
+    graph_mode = None
     for it in range(args.iters):
-        pl, vl, ent, prl = tr.iteration()
+        mode = scheduled_mode(args, tr.n_iter)
+        if args.graph:
+            if graph_mode != mode:
+                tr.capture(training_mode=mode, warmup=1)
+                graph_mode = mode
+            pl, vl, ent, prl = tr.replay()
+        else:
+            pl, vl, ent, prl = tr.iteration(training_mode=mode)
         if rank == 0 and (it % 10 == 0 or it == args.iters - 1):
             torch.cuda.synchronize()
             sps = (it + 1) * tr.env_steps_per_iteration() * world / (time.time() - t0)
-            print('iter %d  policy_loss %.4f %.4f  value_loss %.4f %.4f  pred_loss %.4f  reward %.4f  env-steps/s %.3e' % (
-                it, pl[:, 0].mean(), pl[:, 1].mean(), vl[:, 0].mean(), vl[:, 1].mean(), prl.mean(), tr.player.rew_buf[:, :, 0].mean(), sps))
+            print('iter %d  mode %d  policy_loss %.4f %.4f  value_loss %.4f %.4f  pred_loss %.4f  reward %.4f  env-steps/s %.3e' % (
+                it, mode, pl[:, 0].mean(), pl[:, 1].mean(), vl[:, 0].mean(), vl[:, 1].mean(), prl.mean(), tr.player.rew_buf[:, :, 0].mean(), sps), flush=True)
+        if args.eval_every > 0 and tr.n_iter % args.eval_every == 0:
+            evaluate()
+        if tr.n_iter > args.max_step:  # test.py:130-134
+            break
+    evaluate()
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()

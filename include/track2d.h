@@ -274,7 +274,8 @@ int track2d_embed_add(const float *x_dev, int64_t ld, float *out_dev, int64_t ou
 /* Agent.optimize's recursions and loss gradients for all envs (player_util.py:117-145): from the packed head outputs of both
  * agents (out8_*_dev [T+1][E][8], slot T = the bootstrap forward), actions [T][E][2], rewards [T][E][2], done [T][E]:
  * n-step returns and GAE cut at episode ends, then dL/d(out8) -> dout8_*_dev [T][E][8] for L = scale * sum_e sum_t of the
- * reference's per-step loss terms of the agents with train_k != 0 (+ the aux L1 when use_aux), and the per-env statistics
+ * reference's per-step loss terms of the agents with train_k != 0 (+ the aux L1 when use_aux == 2; use_aux == 1 only reports it, 0 = the
+ * target has no reward_aux head), and the per-env statistics
  * stats_dev [7][E] = policy_loss 0/1, value_loss 0/1, entropy 0/1, pred_loss.  returns_dev / gae_dev [T][E][2] optional. */
 int track2d_a3c_loss_grad(const float *out8_0_dev, const float *out8_1_dev, float *dout8_0_dev, float *dout8_1_dev, const int32_t *actions_dev,
                           const float *rewards_dev, const uint8_t *done_dev, float *stats_dev, float *returns_dev, float *gae_dev, int32_t T,

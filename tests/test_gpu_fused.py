@@ -126,7 +126,7 @@ def test_a3c_loss_grad_matches_autograd(lib, mode, use_aux):
     ret, gae = torch.zeros(T, E, 2, device=DEV), torch.zeros(T, E, 2, device=DEV)
     scale = 1.0 / E
     _lib.check(lib.track2d_a3c_loss_grad(_p(out8[0]), _p(out8[1]), _p(dout[0]), _p(dout[1]), _p(actions), _p(rew), _p(done), _p(stats), _p(ret), _p(gae), T, E,
-                                         gamma, tau, w_ent[0], w_ent[1], scale, int(mode in (-1, 0)), int(mode in (-1, 1)), int(use_aux and mode != 0), _stream()), lib)
+                                         gamma, tau, w_ent[0], w_ent[1], scale, int(mode in (-1, 0)), int(mode in (-1, 1)), 2 if (use_aux and mode != 0) else 1, _stream()), lib)
     # reference
     vals = torch.stack([out8[0][:, :, 4], out8[1][:, :, 4]], 2)  # (T+1, E, 2)
     R, G, vnext = vals[T].detach().clone(), torch.zeros(E, 2, device=DEV), vals[T].detach().clone()
@@ -182,7 +182,7 @@ def test_lstm_heads_backward_matches_autograd(lib, E):
     h2 = so * torch.tanh(c2)
     keep = (1 - done.float()).unsqueeze(1)
     obj = ((h2 @ w_head.t()) * dout8).sum() + (h2 * dh_rec * keep).sum() + (c2 * dc_rec * keep).sum()
-    dg_ref, dc_ref = torch.autograd.grad(obj, [gates, c_prev])
+    dg_ref, dc_ref = torch.autograd.grad(obj, [gates, c_prev], retain_graph=True)
     act = torch.cat([si, sf, tg, so], 1).detach().contiguous()
     dgates = torch.zeros(E, 512, device=DEV)
     dc = dc_rec.clone()

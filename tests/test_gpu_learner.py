@@ -77,7 +77,7 @@ def test_batched_learner_matches_oracle(env_id, network, aux, mode):
             forced_all.append(f)
             p.action_train(torch.from_numpy(f).cuda())
         boot = rs.randint(0, 4, size=(E, 2))
-        obs = p.obs_buf.detach().cpu().clone()
+        obs = p.obs_buf.detach().float().cpu().clone()  # (uint8 observation slots on the fused path)
         rewards = p.rew_buf.detach().cpu().clone()
         dones = p.done_buf.cpu().numpy().astype(bool).copy()
         n_done += int(dones.sum())
@@ -228,7 +228,7 @@ def test_cuda_graph_replay_of_the_whole_iteration():
     assert tr.env.counters()[0] > eps0  # episodes keep finishing and resetting inside the graph
     ctr = tr.env.get_agents()[1]
     assert ctr[:, 1].max() > 20, "elapsed-step counters must carry across replays"
-    assert float(tr.player.hx_store.abs().max()) > 0
+    assert float(tr.player.hxs.abs().max()) > 0
     assert tr.env.status() == 0
     # eager and replay agree statistically: the same trainer continues eagerly without a jump in the losses
     pl, vl, ent, prl = tr.iteration()
