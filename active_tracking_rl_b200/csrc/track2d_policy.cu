@@ -22,8 +22,26 @@
 
 void t2d_set_error(const char *fmt, ...);
 void t2d_count_launches(int n);
+// track2d_conv_tc.cu: the same stack with conv2 on the tensor cores
+cudaError_t t2d_conv_tc_forward(const void *x, int x_is_u8, int64_t xs, int64_t n, const float *w1, const float *b1, const float *w2, const float *b2, float *y2,
+                                cudaStream_t st);
+cudaError_t t2d_conv_tc_backward(const void *x, int x_is_u8, int64_t xs, const float *y2, const float *gy2, int64_t n, const float *w1, const float *b1,
+                                 const float *w2, float *dw1, float *db1, float *dw2, float *db2, cudaStream_t st);
+
+#include <stdlib.h>
+#include <string.h>
 
 namespace {
+
+// T2D_CONV_IMPL=simt selects the FP32 CUDA-core kernels of this file (A/B measurements); default: tcgen05 (track2d_conv_tc.cu)
+bool conv_use_tc() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("T2D_CONV_IMPL");
+        v = (e && strcmp(e, "simt") == 0) ? 0 : 1;
+    }
+    return v == 1;
+}
 
 // Blackwell's packed fp32 FMA (fma.rn.f32x2 -> FFMA2): two independent round-to-nearest FMAs per instruction, i.e. the same
 // arithmetic as two fmaf() at half the issue slots (a scalar FFMA occupies the FMA pipe for 2 cycles per warp either way).
@@ -333,8 +351,10 @@ extern "C" int track2d_maze_conv_forward_ex(const void *x, int32_t x_is_u8, int6
         return T2D_E_INVALID;
     }
     t2d_count_launches(1);
-    cudaError_t err = x_is_u8 ? conv_fwd_launch((const uint8_t *)x, x_stride, n_images, w1, b1, w2, b2, y2, (cudaStream_t)stream)
-                              : conv_fwd_launch((const float *)x, x_stride, n_images, w1, b1, w2, b2, y2, (cudaStream_t)stream);
+    cudaError_t err;
+    if (conv_use_tc()) err = t2d_conv_tc_forward(x, x_is_u8, x_stride, n_images, w1, b1, w2, b2, y2, (cudaStream_t)stream);
+    else err = x_is_u8 ? conv_fwd_launch((const uint8_t *)x, x_stride, n_images, w1, b1, w2, b2, y2, (cudaStream_t)stream)
+                       : conv_fwd_launch((const float *)x, x_stride, n_images, w1, b1, w2, b2, y2, (cudaStream_t)stream);
     if (err != cudaSuccess) {
         t2d_set_error("track2d_maze_conv_forward: %s", cudaGetErrorString(err));
         return T2D_E_CUDA;
@@ -349,9 +369,15 @@ extern "C" int track2d_maze_conv_backward_ex(const void *x, int32_t x_is_u8, int
         t2d_set_error("track2d_maze_conv_backward: bad argument");
         return T2D_E_INVALID;
     }
-    t2d_count_launches(1);
-    cudaError_t err = x_is_u8 ? conv_bwd_launch((const uint8_t *)x, x_stride, y2, gy2, n_images, w1, b1, w2, dw1, db1, dw2, db2, (cudaStream_t)stream)
-                              : conv_bwd_launch((const float *)x, x_stride, y2, gy2, n_images, w1, b1, w2, dw1, db1, dw2, db2, (cudaStream_t)stream);
+    cudaError_t err;
+    if (conv_use_tc()) {
+        t2d_count_launches(2);
+        err = t2d_conv_tc_backward(x, x_is_u8, x_stride, y2, gy2, n_images, w1, b1, w2, dw1, db1, dw2, db2, (cudaStream_t)stream);
+    } else {
+        t2d_count_launches(1);
+        err = x_is_u8 ? conv_bwd_launch((const uint8_t *)x, x_stride, y2, gy2, n_images, w1, b1, w2, dw1, db1, dw2, db2, (cudaStream_t)stream)
+                      : conv_bwd_launch((const float *)x, x_stride, y2, gy2, n_images, w1, b1, w2, dw1, db1, dw2, db2, (cudaStream_t)stream);
+    }
     if (err != cudaSuccess) {
         t2d_set_error("track2d_maze_conv_backward: %s", cudaGetErrorString(err));
         return T2D_E_CUDA;

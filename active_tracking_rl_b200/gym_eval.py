@@ -79,6 +79,11 @@ def write_csv(path, row):
         w.writerows([row])
 
 
+def _compact(sd):
+    """the parameters are views into SharedAdam's flat buffer; torch.save would write the WHOLE underlying storage for each of them"""
+    return {k: v.detach().clone() for k, v in sd.items()}
+
+
 class Evaluator(object):
     """test.py:56-134 without the process: evaluate on --env-base, keep the best tracker return, write checkpoints,
     and say which training mode comes next (init_step schedule, test.py:84-91)."""
@@ -96,10 +101,10 @@ class Evaluator(object):
             paths = ('all-best-{0}.dat'.format(n_iter), 'tracker-best.dat', 'target-best.dat')
         else:
             paths = ('all-new.dat', 'tracker-new.dat', 'target-new.dat')
-        torch.save(model.state_dict(), os.path.join(self.log_dir, paths[0]))
+        torch.save(_compact(model.state_dict()), os.path.join(self.log_dir, paths[0]))
         if getattr(self.args, 'split', False):
-            torch.save(model.player0.state_dict(), os.path.join(self.log_dir, paths[1]))
-            torch.save(model.player1.state_dict(), os.path.join(self.log_dir, paths[2]))
+            torch.save(_compact(model.player0.state_dict()), os.path.join(self.log_dir, paths[1]))
+            torch.save(_compact(model.player1.state_dict()), os.path.join(self.log_dir, paths[2]))
         stats["checkpoint"] = paths[0]
         stats["next_train_mode"] = 0 if n_iter < self.args.init_step else self.args.train_mode
         stats["stop"] = n_iter > self.args.max_step

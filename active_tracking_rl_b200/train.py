@@ -174,7 +174,7 @@ class Trainer(object):
         return self.args.num_steps * self.args.num_envs
 
     def save(self, path):
-        torch.save(self.model.state_dict(), path)
+        torch.save({k: v.detach().clone() for k, v in self.model.state_dict().items()}, path)  # (views of one flat buffer: clone)
 
 
 def scheduled_mode(args, n_iter):

@@ -157,7 +157,8 @@ def test_training_runs_and_improves_value_loss():
 
 @pytest.mark.parametrize("N", [1, 7, 8, 1000, 5003])
 def test_fused_conv_stack_matches_torch(N):
-    """csrc/track2d_policy.cu vs F.conv2d in float64: forward 1e-5, weight gradients 1e-4 relative (fp32 sums over N)."""
+    """the fused conv stack (conv2 on tcgen05 with the 3xTF32 split: |err| <= ~2e-6 * sum|a||b|) vs F.conv2d in float64: forward 3e-5,
+    weight gradients 1e-4 relative (fp32 sums over N)."""
     import torch.nn.functional as F
     from active_tracking_rl_b200.model import _MazeConvStack
     g = torch.Generator(device="cuda").manual_seed(N)
@@ -173,7 +174,7 @@ def test_fused_conv_stack_matches_torch(N):
     W1, B1, W2, B2 = [d(t).requires_grad_(True) for t in (w1, b1, w2, b2)]
     yr = F.relu(F.conv2d(F.relu(F.conv2d(x.double(), W1, B1, stride=2, padding=1)), W2, B2, stride=2, padding=1)).reshape(N, 512)
     gr = torch.autograd.grad(yr, [W1, B1, W2, B2], gy.double())
-    assert torch.allclose(y.double(), yr, rtol=1e-5, atol=1e-5), (y.double() - yr).abs().max()
+    assert torch.allclose(y.double(), yr, rtol=3e-5, atol=3e-5), (y.double() - yr).abs().max()
     for a, b, name in zip(grads, gr, ("w1", "b1", "w2", "b2")):
         scale = float(b.abs().max()) + 1e-6
         assert float((a.double() - b).abs().max()) <= 1e-4 * scale + 1e-5, (name, float((a.double() - b).abs().max()), scale)
