@@ -5,10 +5,10 @@
 // conv2 is 73.7 k of the stack's 80.8 k MAC per image and is an implicit GEMM: rows = (image, output position), reduction =
 // (tap, input channel) = 144, columns = 32 output channels.  A CTA (one per SM, persistent) works on tiles of 8 images = 128 rows:
 //
-//   warps 5..12   conv1    warp = image, lane = (output row, channel quad): 7 x 4 outputs x 9 FMA on the CUDA cores from a zero-bordered
+//   warps 5..11   conv1    thread = (image, output row, channel quad): 7 x 4 outputs x 9 FMA on the CUDA cores from a zero-bordered
 //                          image tile (weights in registers), written channel-last into shared memory (y1s, double-buffered) as 16-byte
 //                          stores; the next tile's pixels are prefetched into registers
-//   warps 13..20  gather   per tap (ki, kj): the 128 x 16 slice of the im2col matrix = one 16-byte copy per (row, 4 channels) out of y1s
+//   warps 12..19  gather   per tap (ki, kj): the 128 x 16 slice of the im2col matrix = one 16-byte copy per (row, 4 channels) out of y1s
 //                          (zeros outside the 7x7 map), split on the fly into hi = tf32(x), lo = x - hi, stored as two K-major
 //                          SWIZZLE_64B operand blocks; 4-stage ring, fence.proxy.async + mbarrier per stage
 //   warp 4        MMA      per stage 2 x 3 tcgen05.mma kind::tf32 (128 x 32 x 8: A_lo B_hi, A_hi B_lo, A_hi B_hi -- fp32-accurate 3xTF32)
@@ -42,8 +42,8 @@ constexpr int B_BLOCK = 32 * 64;               // one tap of the weights: 32 out
 constexpr int B_BYTES = 2 * 9 * B_BLOCK;       // hi[9] | lo[9]
 constexpr int Y1_IMG = 49 * 16 + 4;            // floats per image, channel-last [pos][ic]; the +4 puts image i on banks 4i
 constexpr int Y1_BYTES = IMGS * Y1_IMG * 4;
-constexpr int XS_IMG = 15 * 15;                // zero-bordered input image
-constexpr int XS_BYTES = IMGS * XS_IMG * 4;
+constexpr int XS_IMG = 15 * 16;                // zero-bordered input image as BYTES: 15 rows of 15 (+1) pixels = 16 bytes per row
+constexpr int XS_BYTES = IMGS * XS_IMG;
 constexpr int OUT_IMG = 512 + 4;               // staged output row of one image
 constexpr int OUT_BYTES = IMGS * OUT_IMG * 4;
 constexpr int OFF_B = 0;
@@ -53,16 +53,44 @@ constexpr int OFF_XS = OFF_Y1 + 2 * Y1_BYTES;
 constexpr int OFF_OUT = OFF_XS + 2 * XS_BYTES;
 constexpr int OFF_BAR = OFF_OUT + OUT_BYTES;
 constexpr int FWD_SMEM = OFF_BAR + 256 + 1024 /* alignment slack */;
-constexpr int EPI_WARPS = 4, MMA_WARP = 4, C1_WARP0 = 5, C1_WARPS = 8, G_WARP0 = 13, G_WARPS = 8;
-constexpr int FWD_THREADS = (G_WARP0 + G_WARPS) * 32;  // 672
+// 20 warps: registers are allocated to warps in groups of 4, so 21 warps would cap a thread at 80 registers; 20 leave 96
+constexpr int EPI_WARPS = 4, MMA_WARP = 4, C1_WARP0 = 5, C1_WARPS = 7, G_WARP0 = 12, G_WARPS = 8;
+constexpr int FWD_THREADS = (G_WARP0 + G_WARPS) * 32;  // 640
 constexpr int TMEM_COLS = 64;
 static_assert(OFF_A % 1024 == 0 && OFF_Y1 % 16 == 0 && OFF_XS % 16 == 0 && OFF_OUT % 16 == 0 && OFF_BAR % 8 == 0, "shared-memory layout");
 static_assert(FWD_SMEM <= 227 * 1024, "shared memory");
 
+// The observation cells are small integers (0, 1, 2, 4): the image tile lives in shared memory as bytes, a thread fetches its
+// 3 x 15 window with three 16-byte loads and expands pixels in registers (one PRMT + one FADD each, exact for 0..255).
 template <typename XT>
-__device__ __forceinline__ float load_px(const XT *__restrict__ x, long long xs, long long N, long long n0, int e) {
+__device__ __forceinline__ uint32_t load_px(const XT *__restrict__ x, long long xs, long long N, long long n0, int e) {
     const int img = e / 169, c = e - img * 169;
-    return (e < IMGS * 169 && n0 + img < N) ? (float)x[(n0 + img) * xs + c] : 0.f;
+    return (e < IMGS * 169 && n0 + img < N) ? (uint32_t)x[(n0 + img) * xs + c] : 0u;
+}
+__device__ __forceinline__ void store_px(uint8_t *xs8, int e, uint32_t v) {
+    if (e < IMGS * 169) {
+        const int im = e / 169, c = e - im * 169, r = c / 13, q = c - r * 13;
+        xs8[im * XS_IMG + (r + 1) * 16 + q + 1] = (uint8_t)v;
+    }
+}
+template <int COL>
+__device__ __forceinline__ float win_px(const uint4 &w) {
+    const uint32_t word = COL < 4 ? w.x : (COL < 8 ? w.y : (COL < 12 ? w.z : w.w));
+    return __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7540u | (uint32_t)(COL & 3))) - 8388608.f;  // 2^23 + b, minus 2^23
+}
+// y1 (conv1 + ReLU) of output row `row`, column J, channels 4 q .. 4 q + 3, from the thread's 3 x 15 pixel window
+template <int J, typename W>
+__device__ __forceinline__ float4 conv1_at(const uint4 (&win)[3], const W &w, const float4 &b) {
+    float4 a = b;
+#define T2D_TAP(KI, KJ)                                   \
+    {                                                     \
+        const float v = win_px<2 * J + KJ>(win[KI]);      \
+        const float4 ww = w[KI * 3 + KJ];                 \
+        a.x = fmaf(v, ww.x, a.x); a.y = fmaf(v, ww.y, a.y); a.z = fmaf(v, ww.z, a.z); a.w = fmaf(v, ww.w, a.w); \
+    }
+    T2D_TAP(0, 0) T2D_TAP(0, 1) T2D_TAP(0, 2) T2D_TAP(1, 0) T2D_TAP(1, 1) T2D_TAP(1, 2) T2D_TAP(2, 0) T2D_TAP(2, 1) T2D_TAP(2, 2)
+#undef T2D_TAP
+    return a;
 }
 
 template <typename XT>
@@ -102,7 +130,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) conv_tc_fwd_kernel(const XT *_
         *reinterpret_cast<float *>(sm + OFF_B + off) = hi;
         *reinterpret_cast<float *>(sm + OFF_B + 9 * B_BLOCK + off) = lo;
     }
-    for (int i = threadIdx.x; i < 2 * IMGS * XS_IMG; i += FWD_THREADS) reinterpret_cast<float *>(sm + OFF_XS)[i] = 0.f;  // borders stay zero
+    for (int i = threadIdx.x; i < 2 * XS_BYTES / 4; i += FWD_THREADS) reinterpret_cast<uint32_t *>(sm + OFF_XS)[i] = 0u;  // borders stay zero
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -140,33 +168,24 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) conv_tc_fwd_kernel(const XT *_
         }
     } else if (warp >= C1_WARP0) {
         // ===== conv1 + ReLU on the CUDA cores =====
-        // warp = image; lane = (output row i, channel quad q): 7 positions x 4 channels per thread, weights in registers for the
-        // whole kernel, every pixel read from shared memory serves 4 FMAs, results leave as 16-byte channel-last stores
+        // thread = (image, output row i, channel quad q): 7 positions x 4 channels per thread, weights in registers for the
+        // whole kernel, the 3 x 15 pixel window in 12 registers, results leave as 16-byte channel-last stores
         const int ct = threadIdx.x - C1_WARP0 * 32;
-        const int img = ct >> 5, row = (ct >> 2) & 7, q = ct & 3;
-        float w[4][9], bias[4];
+        const int img = ct / 28, row = (ct % 28) >> 2, q = ct & 3;  // 7 warps = 8 images x 7 rows x 4 channel quads (28 = 0 mod 4)
+        float4 w[9], bias;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-#pragma unroll
-            for (int k = 0; k < 9; ++k) w[c][k] = __ldg(w1 + (4 * q + c) * 9 + k);
-            bias[c] = __ldg(b1 + 4 * q + c);
-        }
+        for (int k = 0; k < 9; ++k) w[k] = make_float4(__ldg(w1 + (4 * q) * 9 + k), __ldg(w1 + (4 * q + 1) * 9 + k), __ldg(w1 + (4 * q + 2) * 9 + k), __ldg(w1 + (4 * q + 3) * 9 + k));
+        bias = make_float4(__ldg(b1 + 4 * q), __ldg(b1 + 4 * q + 1), __ldg(b1 + 4 * q + 2), __ldg(b1 + 4 * q + 3));
         constexpr int PRE = (IMGS * 169 + C1_WARPS * 32 - 1) / (C1_WARPS * 32);  // 6
-        float pre[PRE];
+        uint32_t pre[PRE];
 #pragma unroll
         for (int j = 0; j < PRE; ++j) pre[j] = load_px(x, xs, N, (long long)blockIdx.x * IMGS, ct + C1_WARPS * 32 * j);
         int it = 0;
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int buf = it & 1;
-            float *xsb = reinterpret_cast<float *>(sm + OFF_XS + buf * XS_BYTES);
+            uint8_t *xs8 = sm + OFF_XS + buf * XS_BYTES;
 #pragma unroll
-            for (int j = 0; j < PRE; ++j) {
-                const int e = ct + C1_WARPS * 32 * j;
-                if (e < IMGS * 169) {
-                    const int im = e / 169, c = e - im * 169, r = c / 13, qq = c - r * 13;
-                    xsb[im * XS_IMG + (r + 1) * 15 + qq + 1] = pre[j];
-                }
-            }
+            for (int j = 0; j < PRE; ++j) store_px(xs8, ct + C1_WARPS * 32 * j, pre[j]);
             const long long next = tile + gridDim.x;
             if (next < n_tiles) {
 #pragma unroll
@@ -175,23 +194,17 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) conv_tc_fwd_kernel(const XT *_
             bar_sync(1, C1_WARPS * 32);
             mbar_wait(bar_y1e + 8 * buf, ((uint32_t)(it >> 1) & 1u) ^ 1u);
             if (row < 7) {
-                const float *xi = xsb + img * XS_IMG + (2 * row) * 15;
+                uint4 win[3];
+#pragma unroll
+                for (int ki = 0; ki < 3; ++ki) win[ki] = *reinterpret_cast<const uint4 *>(xs8 + img * XS_IMG + (2 * row + ki) * 16);
                 float *yo = reinterpret_cast<float *>(sm + OFF_Y1 + buf * Y1_BYTES) + img * Y1_IMG + (row * 7) * 16 + 4 * q;
-#pragma unroll
-                for (int j = 0; j < 7; ++j) {
-                    float a0 = bias[0], a1 = bias[1], a2 = bias[2], a3 = bias[3];
-#pragma unroll
-                    for (int ki = 0; ki < 3; ++ki)
-#pragma unroll
-                        for (int kj = 0; kj < 3; ++kj) {
-                            const float v = xi[ki * 15 + 2 * j + kj];
-                            a0 = fmaf(v, w[0][ki * 3 + kj], a0);
-                            a1 = fmaf(v, w[1][ki * 3 + kj], a1);
-                            a2 = fmaf(v, w[2][ki * 3 + kj], a2);
-                            a3 = fmaf(v, w[3][ki * 3 + kj], a3);
-                        }
-                    *reinterpret_cast<float4 *>(yo + j * 16) = make_float4(fmaxf(a0, 0.f), fmaxf(a1, 0.f), fmaxf(a2, 0.f), fmaxf(a3, 0.f));
-                }
+#define T2D_POS(J)                                                                                          \
+    {                                                                                                       \
+        const float4 a = conv1_at<J>(win, w, bias);                                                         \
+        *reinterpret_cast<float4 *>(yo + J * 16) = make_float4(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f), fmaxf(a.z, 0.f), fmaxf(a.w, 0.f)); \
+    }
+                T2D_POS(0) T2D_POS(1) T2D_POS(2) T2D_POS(3) T2D_POS(4) T2D_POS(5) T2D_POS(6)
+#undef T2D_POS
             }
             mbar_arrive(bar_y1f + 8 * buf);
         }
@@ -276,11 +289,11 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) conv_tc_fwd_kernel(const XT *_
 //   warps 0..3    epilogue   tcgen05.ld of dCOL, col2im into dy1s in four tap phases (inside a phase every cell gets at most one
 //                            contribution, so plain read-modify-writes are race free and the summation order is fixed)
 //   warp 4        MMA
-//   warps 5..12   conv1      recompute (ReLU mask kept in a register), later dz1 = dy1 * mask -> dW1, db1
-//   warps 13..20  gather     dz2 = gy2 * (y2 > 0) staged transposed, its two operand images, and the COL^T stages out of y1s
+//   warps 5..11   conv1      recompute (ReLU mask kept in a register), later dz1 = dy1 * mask -> dW1, db1
+//   warps 12..19  gather     dz2 = gy2 * (y2 > 0) staged transposed, its two operand images, and the COL^T stages out of y1s
 constexpr int BW2_BLOCK = 144 * 64;                 // W2 as the dCOL B operand: 144 rows (tap, ic) x 16 output channels
 constexpr int BW2_BYTES = 4 * BW2_BLOCK;            // [hi | lo][2 reduction blocks]
-constexpr int BSTAGES = 3;
+constexpr int BSTAGES = 2;
 constexpr int BA_SBO = 5 * 512;                     // COL^T: 144 rows = 4.5 atoms of 32 rows per group of 4 reduction indices
 constexpr int BA_PLANE = 4 * BA_SBO;                // 16 reduction indices
 constexpr int BB_SBO = 512;                         // dz2 as MN-major B: 32 rows = one atom per group
@@ -296,9 +309,9 @@ constexpr int BOFF_RING = BOFF_W2 + BW2_BYTES;                 // 36,864
 constexpr int BOFF_DZA = BOFF_RING + BSTAGES * BSTAGE_BYTES;   // 110,592
 constexpr int BOFF_DZT = BOFF_DZA + DZA_BYTES;
 constexpr int BOFF_Y1 = BOFF_DZT + DZT_BYTES;
-constexpr int BOFF_DY = BOFF_Y1 + Y1_BYTES;
-constexpr int BOFF_XS = BOFF_DY + DY_BYTES;
-constexpr int BOFF_BAR = (BOFF_XS + XS_BYTES + 15) / 16 * 16;
+constexpr int BOFF_DY = BOFF_Y1 + 2 * Y1_BYTES;                // y1s and the pixel tile are double-buffered: conv1 runs one tile ahead
+constexpr int BOFF_XS = BOFF_DY + (DY_BYTES + 15) / 16 * 16;
+constexpr int BOFF_BAR = BOFF_XS + 2 * XS_BYTES;
 constexpr int BWD_SMEM = BOFF_BAR + 256 + 640 + 1024;  // barriers, conv1 weights + biases, alignment slack
 constexpr int BWD_THREADS = FWD_THREADS;
 constexpr int BTMEM_COLS = 512, TM_DW2 = 0, TM_DCOL = 64, TM_DCOL_STRIDE = 160;
@@ -315,16 +328,18 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) conv_tc_bwd_kernel(const XT *_
     const uint32_t smem0 = (raw0 + 1023u) & ~1023u;
     uint8_t *sm = smem_raw + (smem0 - raw0);
     const uint32_t bars = smem0 + BOFF_BAR;
-    const uint32_t bar_y1f = bars, bar_y1e = bars + 8, bar_dyf = bars + 16, bar_dye = bars + 24, bar_dzf = bars + 32, bar_dze = bars + 40,
-                   bar_full = bars + 48, bar_empty = bar_full + 8 * BSTAGES, bar_accf = bar_empty + 8 * BSTAGES, bar_acce = bar_accf + 16,
+    const uint32_t bar_y1f = bars, bar_y1e = bars + 16, bar_dyf = bars + 32, bar_dye = bars + 40, bar_dzf = bars + 48, bar_dze = bars + 56,
+                   bar_full = bars + 64, bar_empty = bar_full + 8 * BSTAGES, bar_accf = bar_empty + 8 * BSTAGES, bar_acce = bar_accf + 16,
                    bar_dw2 = bar_acce + 16, tmem_slot = bar_dw2 + 8;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long n_tiles = (N + IMGS - 1) / IMGS;
     float *my_part = part + (long long)blockIdx.x * PART_FLOATS;
 
     if (threadIdx.x == 0) {
-        mbar_init(bar_y1f, C1_WARPS * 32);
-        mbar_init(bar_y1e, G_WARPS * 32);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(bar_y1f + 8 * b, C1_WARPS * 32);
+            mbar_init(bar_y1e + 8 * b, G_WARPS * 32);
+        }
         mbar_init(bar_dyf, EPI_WARPS * 32);
         mbar_init(bar_dye, C1_WARPS * 32);
         mbar_init(bar_dzf, G_WARPS * 32);
@@ -350,8 +365,13 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) conv_tc_bwd_kernel(const XT *_
         *reinterpret_cast<float *>(sm + BOFF_W2 + off) = hi;
         *reinterpret_cast<float *>(sm + BOFF_W2 + 2 * BW2_BLOCK + off) = lo;
     }
-    for (int i = threadIdx.x; i < 160; i += BWD_THREADS) reinterpret_cast<float *>(sm + BOFF_BAR + 256)[i] = i < 144 ? w1[i] : b1[i - 144];
-    for (int i = threadIdx.x; i < IMGS * XS_IMG; i += BWD_THREADS) reinterpret_cast<float *>(sm + BOFF_XS)[i] = 0.f;
+    for (int i = threadIdx.x; i < 160; i += BWD_THREADS) {  // conv1 weights as [q][k][4 channels], then biases [q][4]
+        float v;
+        if (i < 144) { const int qq = i / 36, k = (i % 36) / 4, c = i & 3; v = w1[(4 * qq + c) * 9 + k]; }
+        else v = b1[i - 144];
+        reinterpret_cast<float *>(sm + BOFF_BAR + 256)[i] = v;
+    }
+    for (int i = threadIdx.x; i < 2 * XS_BYTES / 4; i += BWD_THREADS) reinterpret_cast<uint32_t *>(sm + BOFF_XS)[i] = 0u;
     for (int i = threadIdx.x; i < IMGS * DY_IMG; i += BWD_THREADS) reinterpret_cast<float *>(sm + BOFF_DY)[i] = 0.f;
     for (int i = threadIdx.x; i < BSTAGES * BSTAGE_BYTES / 4; i += BWD_THREADS) reinterpret_cast<float *>(sm + BOFF_RING)[i] = 0.f;  // rows 144..159 stay 0
     fence_proxy_async();
@@ -410,7 +430,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) conv_tc_bwd_kernel(const XT *_
             fence_proxy_async();
             mbar_arrive(bar_dzf);
             // (c) the COL^T stages: 16 rows of the tile (two output positions x 8 images) per stage
-            mbar_wait(bar_y1f, (uint32_t)it & 1u);
+            const int ybuf = it & 1;
+            mbar_wait(bar_y1f + 8 * ybuf, (uint32_t)(it >> 1) & 1u);
 #pragma unroll 1
             for (int s8 = 0; s8 < 8; ++s8, ++ist) {
                 const int s = ist % BSTAGES;
@@ -425,7 +446,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) conv_tc_bwd_kernel(const XT *_
                         const int opos = 2 * s8 + ol, ki = tap / 3, kj = tap - ki * 3;
                         const int r = 2 * (opos >> 2) + ki - 1, cc = 2 * (opos & 3) + kj - 1;
                         float4 v = make_float4(0.f, 0.f, 0.f, 0.f), hi, lo;
-                        if (r >= 0 && r < 7 && cc >= 0 && cc < 7) v = lds128(smem0 + BOFF_Y1 + (uint32_t)(img * Y1_IMG + (r * 7 + cc) * 16 + c * 4) * 4u);
+                        if (r >= 0 && r < 7 && cc >= 0 && cc < 7) v = lds128(smem0 + BOFF_Y1 + ybuf * Y1_BYTES + (uint32_t)(img * Y1_IMG + (r * 7 + cc) * 16 + c * 4) * 4u);
                         split4(v, hi, lo);
                         const uint32_t off = mnmajor_off(kk, c36, BA_SBO);
                         sts128(st + off, hi);
@@ -444,7 +465,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) conv_tc_bwd_kernel(const XT *_
                 fence_proxy_async();
                 mbar_arrive(bar_full + 8 * s);
             }
-            mbar_arrive(bar_y1e);
+            mbar_arrive(bar_y1e + 8 * ybuf);
             bar_sync(3, G_WARPS * 32);  // dzt is rewritten by the next tile
         }
         // db2: the 8 loader threads of an output channel, added in a fixed order (the ring is scratch once the last MMA has read it)
@@ -460,10 +481,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) conv_tc_bwd_kernel(const XT *_
             my_part[32 * 144 + 144 + 16 + gt] = t;
         }
     } else if (warp >= C1_WARP0) {
-        // ===== conv1 recompute, then dz1 -> dW1 / db1 =====
+        // ===== conv1 recompute (one tile ahead), then dz1 -> dW1 / db1 =====
         const int ct = threadIdx.x - C1_WARP0 * 32;
-        const int img = ct >> 5, row = (ct >> 2) & 7, q = ct & 3;
-        // (the conv1 weights are re-read from shared memory per tile here: the registers hold the 40 gradient accumulators instead)
+        const int img = ct / 28, row = (ct % 28) >> 2, q = ct & 3;  // 7 warps = 8 images x 7 rows x 4 channel quads (28 = 0 mod 4)
+        // the conv1 weights are re-read from shared memory per tile: the registers hold the 40 gradient accumulators
         float aw1[4][9], ab1[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -471,78 +492,84 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) conv_tc_bwd_kernel(const XT *_
             for (int k = 0; k < 9; ++k) aw1[c][k] = 0.f;
             ab1[c] = 0.f;
         }
-        const float *wsm = reinterpret_cast<const float *>(sm + BOFF_BAR + 256) + 4 * q * 9;  // [16][9] weights, then [16] biases
+        const float4 *wsm = reinterpret_cast<const float4 *>(sm + BOFF_BAR + 256) + 9 * q;
+        const float4 *bsm = reinterpret_cast<const float4 *>(sm + BOFF_BAR + 256 + 576) + q;
         constexpr int PRE = (IMGS * 169 + C1_WARPS * 32 - 1) / (C1_WARPS * 32);
-        float pre[PRE];
+        uint32_t pre[PRE];
 #pragma unroll
         for (int j = 0; j < PRE; ++j) pre[j] = load_px(x, xs, N, (long long)blockIdx.x * IMGS, ct + C1_WARPS * 32 * j);
-        float *xsb = reinterpret_cast<float *>(sm + BOFF_XS);
-        int it = 0;
-        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-            bar_sync(1, C1_WARPS * 32);  // every thread is done reading the previous tile's pixels
+        // stage the prefetched pixels of tile number `jt` (and prefetch the following tile), then conv1 + ReLU into y1s[jt & 1]
+        auto conv1_tile = [&](int jt, long long following) -> uint32_t {
+            const int buf = jt & 1;
+            uint8_t *xs8 = sm + BOFF_XS + buf * XS_BYTES;
 #pragma unroll
-            for (int j = 0; j < PRE; ++j) {
-                const int e = ct + C1_WARPS * 32 * j;
-                if (e < IMGS * 169) {
-                    const int im = e / 169, c = e - im * 169, r = c / 13, qq = c - r * 13;
-                    xsb[im * XS_IMG + (r + 1) * 15 + qq + 1] = pre[j];
-                }
-            }
-            const long long next = tile + gridDim.x;
-            if (next < n_tiles) {
+            for (int j = 0; j < PRE; ++j) store_px(xs8, ct + C1_WARPS * 32 * j, pre[j]);
+            if (following < n_tiles) {
 #pragma unroll
-                for (int j = 0; j < PRE; ++j) pre[j] = load_px(x, xs, N, next * IMGS, ct + C1_WARPS * 32 * j);
+                for (int j = 0; j < PRE; ++j) pre[j] = load_px(x, xs, N, following * IMGS, ct + C1_WARPS * 32 * j);
             }
             bar_sync(1, C1_WARPS * 32);
-            mbar_wait(bar_y1e, ((uint32_t)it & 1u) ^ 1u);
+            mbar_wait(bar_y1e + 8 * buf, ((uint32_t)(jt >> 1) & 1u) ^ 1u);
             uint32_t mask = 0u;  // bit 4 j + c: y1 > 0 at column j, channel 4 q + c
-            const float *xi = xsb + img * XS_IMG + (2 * row) * 15;
             if (row < 7) {
-                float *yo = reinterpret_cast<float *>(sm + BOFF_Y1) + img * Y1_IMG + (row * 7) * 16 + 4 * q;
+                uint4 win[3];
 #pragma unroll
-                for (int j = 0; j < 7; ++j) {
-                    const float *bsm = reinterpret_cast<const float *>(sm + BOFF_BAR + 256) + 144 + 4 * q;
-                    float a0 = bsm[0], a1 = bsm[1], a2 = bsm[2], a3 = bsm[3];
-#pragma unroll
-                    for (int ki = 0; ki < 3; ++ki)
-#pragma unroll
-                        for (int kj = 0; kj < 3; ++kj) {
-                            const float v = xi[ki * 15 + 2 * j + kj];
-                            a0 = fmaf(v, wsm[ki * 3 + kj], a0);
-                            a1 = fmaf(v, wsm[9 + ki * 3 + kj], a1);
-                            a2 = fmaf(v, wsm[18 + ki * 3 + kj], a2);
-                            a3 = fmaf(v, wsm[27 + ki * 3 + kj], a3);
-                        }
-                    mask |= ((a0 > 0.f ? 1u : 0u) | (a1 > 0.f ? 2u : 0u) | (a2 > 0.f ? 4u : 0u) | (a3 > 0.f ? 8u : 0u)) << (4 * j);
-                    *reinterpret_cast<float4 *>(yo + j * 16) = make_float4(fmaxf(a0, 0.f), fmaxf(a1, 0.f), fmaxf(a2, 0.f), fmaxf(a3, 0.f));
-                }
+                for (int ki = 0; ki < 3; ++ki) win[ki] = *reinterpret_cast<const uint4 *>(xs8 + img * XS_IMG + (2 * row + ki) * 16);
+                const float4 *w = wsm;  // read per tap from shared memory (broadcast loads): the registers are taken by the accumulators
+                const float4 bias = *bsm;
+                float *yo = reinterpret_cast<float *>(sm + BOFF_Y1 + buf * Y1_BYTES) + img * Y1_IMG + (row * 7) * 16 + 4 * q;
+#define T2D_POS(J)                                                                                          \
+    {                                                                                                       \
+        const float4 a = conv1_at<J>(win, w, bias);                                                         \
+        mask |= ((a.x > 0.f ? 1u : 0u) | (a.y > 0.f ? 2u : 0u) | (a.z > 0.f ? 4u : 0u) | (a.w > 0.f ? 8u : 0u)) << (4 * J); \
+        *reinterpret_cast<float4 *>(yo + J * 16) = make_float4(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f), fmaxf(a.z, 0.f), fmaxf(a.w, 0.f)); \
+    }
+                T2D_POS(0) T2D_POS(1) T2D_POS(2) T2D_POS(3) T2D_POS(4) T2D_POS(5) T2D_POS(6)
+#undef T2D_POS
             }
-            mbar_arrive(bar_y1f);
+            mbar_arrive(bar_y1f + 8 * buf);
+            return mask;
+        };
+        uint32_t mask_cur = conv1_tile(0, (long long)blockIdx.x + gridDim.x), mask_next = 0u;
+        int it = 0;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const long long next = tile + gridDim.x;
+            if (next < n_tiles) {
+                bar_sync(1, C1_WARPS * 32);  // every thread is done with the pixel buffer conv1_tile is about to refill (dW1 of tile it - 1)
+                mask_next = conv1_tile(it + 1, next + gridDim.x);
+            }
             // dy1 of this tile (col2im done by the epilogue warps) -> dz1 = dy1 * (y1 > 0) -> dW1, db1; the cells are zeroed for the next tile
             mbar_wait_backoff(bar_dyf, (uint32_t)it & 1u);
             if (row < 7) {
+                const uint8_t *xs8 = sm + BOFF_XS + (it & 1) * XS_BYTES;
+                uint4 win[3];
+#pragma unroll
+                for (int ki = 0; ki < 3; ++ki) win[ki] = *reinterpret_cast<const uint4 *>(xs8 + img * XS_IMG + (2 * row + ki) * 16);
                 float *dy = reinterpret_cast<float *>(sm + BOFF_DY) + img * DY_IMG + (row * 7) * DY_POS + 4 * q;
-#pragma unroll
-                for (int j = 0; j < 7; ++j) {
-                    float dz[4];
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const float d = dy[j * DY_POS + c];
-                        dy[j * DY_POS + c] = 0.f;
-                        dz[c] = ((mask >> (4 * j + c)) & 1u) ? d : 0.f;
-                        ab1[c] += dz[c];
-                    }
-#pragma unroll
-                    for (int ki = 0; ki < 3; ++ki)
-#pragma unroll
-                        for (int kj = 0; kj < 3; ++kj) {
-                            const float v = xi[ki * 15 + 2 * j + kj];
-#pragma unroll
-                            for (int c = 0; c < 4; ++c) aw1[c][ki * 3 + kj] = fmaf(dz[c], v, aw1[c][ki * 3 + kj]);
-                        }
-                }
+#define T2D_TAP(J, KI, KJ)                                                                     \
+    {                                                                                          \
+        const float v = win_px<2 * J + KJ>(win[KI]);                                           \
+        aw1[0][KI * 3 + KJ] = fmaf(dz[0], v, aw1[0][KI * 3 + KJ]); aw1[1][KI * 3 + KJ] = fmaf(dz[1], v, aw1[1][KI * 3 + KJ]); \
+        aw1[2][KI * 3 + KJ] = fmaf(dz[2], v, aw1[2][KI * 3 + KJ]); aw1[3][KI * 3 + KJ] = fmaf(dz[3], v, aw1[3][KI * 3 + KJ]); \
+    }
+#define T2D_POS(J)                                                                             \
+    {                                                                                          \
+        float dz[4];                                                                           \
+        _Pragma("unroll") for (int c = 0; c < 4; ++c) {                                        \
+            const float d = dy[J * DY_POS + c];                                                \
+            dy[J * DY_POS + c] = 0.f;                                                          \
+            dz[c] = ((mask_cur >> (4 * J + c)) & 1u) ? d : 0.f;                                \
+            ab1[c] += dz[c];                                                                   \
+        }                                                                                      \
+        T2D_TAP(J, 0, 0) T2D_TAP(J, 0, 1) T2D_TAP(J, 0, 2) T2D_TAP(J, 1, 0) T2D_TAP(J, 1, 1) T2D_TAP(J, 1, 2) \
+        T2D_TAP(J, 2, 0) T2D_TAP(J, 2, 1) T2D_TAP(J, 2, 2)                                     \
+    }
+                T2D_POS(0) T2D_POS(1) T2D_POS(2) T2D_POS(3) T2D_POS(4) T2D_POS(5) T2D_POS(6)
+#undef T2D_POS
+#undef T2D_TAP
             }
             mbar_arrive(bar_dye);
+            mask_cur = mask_next;
         }
         // dW1 / db1: per-thread sums -> shared memory -> added in a fixed order (56 (image, row) slots per channel entry)
         __syncthreads();
@@ -559,7 +586,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) conv_tc_bwd_kernel(const XT *_
             const int ch = ct / 10, k = ct - ch * 10, qq = ch >> 2, c = ch & 3;
             float t = 0.f;
             for (int im = 0; im < 8; ++im)
-                for (int rw = 0; rw < 7; ++rw) t += red[(im * 32 + rw * 4 + qq) * 40 + c * 10 + k];
+                for (int rw = 0; rw < 7; ++rw) t += red[(im * 28 + rw * 4 + qq) * 40 + c * 10 + k];
             if (k < 9) my_part[32 * 144 + ch * 9 + k] = t;
             else my_part[32 * 144 + 144 + ch] = t;
         }

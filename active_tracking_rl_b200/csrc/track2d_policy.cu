@@ -352,7 +352,7 @@ extern "C" int track2d_maze_conv_forward_ex(const void *x, int32_t x_is_u8, int6
     }
     t2d_count_launches(1);
     cudaError_t err;
-    if (conv_use_tc()) err = t2d_conv_tc_forward(x, x_is_u8, x_stride, n_images, w1, b1, w2, b2, y2, (cudaStream_t)stream);
+    if (conv_use_tc() && x_is_u8) err = t2d_conv_tc_forward(x, x_is_u8, x_stride, n_images, w1, b1, w2, b2, y2, (cudaStream_t)stream);
     else err = x_is_u8 ? conv_fwd_launch((const uint8_t *)x, x_stride, n_images, w1, b1, w2, b2, y2, (cudaStream_t)stream)
                        : conv_fwd_launch((const float *)x, x_stride, n_images, w1, b1, w2, b2, y2, (cudaStream_t)stream);
     if (err != cudaSuccess) {
@@ -370,7 +370,7 @@ extern "C" int track2d_maze_conv_backward_ex(const void *x, int32_t x_is_u8, int
         return T2D_E_INVALID;
     }
     cudaError_t err;
-    if (conv_use_tc()) {
+    if (conv_use_tc() && x_is_u8) {  // (float32 images -- the autograd path -- keep the CUDA-core kernels)
         t2d_count_launches(2);
         err = t2d_conv_tc_backward(x, x_is_u8, x_stride, y2, gy2, n_images, w1, b1, w2, dw1, db1, dw2, db2, (cudaStream_t)stream);
     } else {
