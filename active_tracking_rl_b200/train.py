@@ -142,6 +142,11 @@ class Trainer(object):
         if self.world_size == 1:
             with torch.cuda.graph(self._graph, stream=side):
                 self._graph_out = self.iteration(mode)
+        elif os.environ.get("T2D_NCCL_IN_GRAPH", "0") == "1":
+            # the all-reduce captured INSIDE the one graph.  The NCCL watchdog thread polls CUDA events, which a capture in the default
+            # "global" error mode forbids process-wide (that was the dead-lock); "thread_local" confines the restriction to this thread.
+            with torch.cuda.graph(self._graph, stream=side, capture_error_mode="thread_local"):
+                self._graph_out = self.iteration(mode)
         else:
             # multi-GPU: two graphs with the NCCL all-reduce launched eagerly between them (capturing the collective itself
             # dead-locked on this image): [rollout, losses, backward] | all-reduce | [SharedAdam, state hand-over]
