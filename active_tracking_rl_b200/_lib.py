@@ -50,6 +50,8 @@ SYMBOLS = {
     "track2d_step_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "track2d_reset_host_u8": (C.c_int, [_vp, _vp, _vp]),
     "track2d_step_host_u8": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "track2d_step_host_begin": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp, _i32]),
+    "track2d_host_chunk_wait": (C.c_int, [_vp, _i32]),
     "track2d_get_maps": (C.c_int, [_vp, _i32, _i32, _vp]),
     "track2d_set_maps": (C.c_int, [_vp, _i32, _i32, _vp]),
     "track2d_get_agents": (C.c_int, [_vp, _i32, _i32, _vp, _vp]),

@@ -44,6 +44,8 @@ struct track2d_env {
     float *d_reward;
     uint8_t *d_done;
     uint8_t *d_mask;
+    cudaEvent_t chunk_ev[16];  // track2d_step_host_begin: one event per observation chunk
+    int n_chunk_ev;
     bool was_reset;
     unsigned long long steps_done;
     std::vector<void *> allocs;
@@ -261,6 +263,7 @@ int track2d_destroy(track2d_env *env) {
     DeviceGuard guard(env->cfg.device);
     cudaDeviceSynchronize();
     for (void *p : env->allocs) cudaFree(p);
+    for (int c = 0; c < env->n_chunk_ev; c++) cudaEventDestroy(env->chunk_ev[c]);
     if (env->own_stream) cudaStreamDestroy(env->own_stream);
     delete env;
     return T2D_OK;
@@ -332,6 +335,35 @@ static int step_host_t(track2d_env *env, const int32_t *actions_host, ObsT *obs_
     return T2D_OK;
 }
 
+// The same transition with the observation D2H issued in n_chunks pieces of consecutive envs; returns after ENQUEUEING.  Chunk c (and,
+// with chunk 0, the reward / done arrays) is in the host buffers once track2d_host_chunk_wait(env, c) returns, so the consumer can
+// process / re-upload chunk c while later chunks are still on the bus (PCIe is full duplex).
+template <typename ObsT>
+static int step_host_begin_t(track2d_env *env, const int32_t *actions_host, ObsT *obs_host, float *reward_host, uint8_t *done_host, int n_chunks) {
+    constexpr bool u8 = sizeof(ObsT) == 1;
+    int rc = ensure_staging(env, u8);
+    if (rc != T2D_OK) return rc;
+    while (env->n_chunk_ev < n_chunks) {
+        T2D_CUDA(cudaEventCreateWithFlags(&env->chunk_ev[env->n_chunk_ev], cudaEventDisableTiming));
+        env->n_chunk_ev++;
+    }
+    cudaStream_t s = env->own_stream;
+    const size_t E = (size_t)env->w.E, cells = (size_t)cells_of(env), per_env = 2 * cells;
+    ObsT *d_obs = u8 ? (ObsT *)env->d_obs8 : (ObsT *)env->d_obs;
+    T2D_CUDA(cudaMemcpyAsync(env->d_actions, actions_host, 2 * E * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    rc = do_step<ObsT>(env, env->d_actions, d_obs, env->d_reward, env->d_done, s);
+    if (rc != T2D_OK) return rc;
+    T2D_CUDA(cudaMemcpyAsync(reward_host, env->d_reward, 2 * E * sizeof(float), cudaMemcpyDeviceToHost, s));
+    T2D_CUDA(cudaMemcpyAsync(done_host, env->d_done, E, cudaMemcpyDeviceToHost, s));
+    for (int c = 0; c < n_chunks; c++) {
+        const size_t e0 = E * (size_t)c / (size_t)n_chunks, e1 = E * (size_t)(c + 1) / (size_t)n_chunks;
+        if (e1 > e0)
+            T2D_CUDA(cudaMemcpyAsync(obs_host + e0 * per_env, d_obs + e0 * per_env, (e1 - e0) * per_env * sizeof(ObsT), cudaMemcpyDeviceToHost, s));
+        T2D_CUDA(cudaEventRecord(env->chunk_ev[c], s));
+    }
+    return T2D_OK;
+}
+
 template <typename ObsT>
 static int reset_host_t(track2d_env *env, const uint8_t *mask_host, ObsT *obs_host) {
     constexpr bool u8 = sizeof(ObsT) == 1;
@@ -371,6 +403,23 @@ int track2d_step_host_u8(track2d_env *env, const int32_t *actions_host, uint8_t 
     T2D_REQUIRE(actions_host, "step_host_u8: actions required");
     DeviceGuard guard(env->cfg.device);
     return step_host_t<uint8_t>(env, actions_host, obs_host, reward_host, done_host);
+}
+
+int track2d_step_host_begin(track2d_env *env, const int32_t *actions_host, void *obs_host, int32_t obs_is_u8, float *reward_host, uint8_t *done_host,
+                            int32_t n_chunks) {
+    T2D_REQUIRE(env, "null handle");
+    T2D_REQUIRE(actions_host && obs_host && reward_host && done_host, "step_host_begin: all four host buffers are required");
+    T2D_REQUIRE(n_chunks >= 1 && n_chunks <= 16, "step_host_begin: 1..16 chunks");
+    DeviceGuard guard(env->cfg.device);
+    return obs_is_u8 ? step_host_begin_t<uint8_t>(env, actions_host, (uint8_t *)obs_host, reward_host, done_host, n_chunks)
+                     : step_host_begin_t<float>(env, actions_host, (float *)obs_host, reward_host, done_host, n_chunks);
+}
+int track2d_host_chunk_wait(track2d_env *env, int32_t chunk) {
+    T2D_REQUIRE(env, "null handle");
+    T2D_REQUIRE(chunk >= 0 && chunk < env->n_chunk_ev, "host_chunk_wait: no such chunk (call track2d_step_host_begin first)");
+    DeviceGuard guard(env->cfg.device);
+    T2D_CUDA(cudaEventSynchronize(env->chunk_ev[chunk]));
+    return T2D_OK;
 }
 
 // ---- state read-back / injection ---------------------------------------------------------------------

@@ -134,6 +134,19 @@ class Track2DVecEnv(object):
         _lib.check(fn(self.h, _ptr(actions_host), _ptr(obs_host), _ptr(reward_host), _ptr(done_host)), self.lib)
         return obs_host, reward_host, done_host
 
+    def step_host_begin(self, actions_host, obs_host, reward_host, done_host, n_chunks=8):
+        """pipelined step_host: enqueue H2D actions, kernels and the D2H of obs in n_chunks pieces; host_chunk_wait(c) blocks until
+        envs chunk_bounds(c, n_chunks) of obs_host (and, with chunk 0, reward / done) have arrived"""
+        _lib.check(self.lib.track2d_step_host_begin(self.h, _ptr(actions_host), _ptr(obs_host), int(obs_host.dtype == torch.uint8), _ptr(reward_host),
+                                                    _ptr(done_host), int(n_chunks)), self.lib)
+
+    def host_chunk_wait(self, chunk):
+        _lib.check(self.lib.track2d_host_chunk_wait(self.h, int(chunk)), self.lib)
+
+    def chunk_bounds(self, chunk, n_chunks):
+        E = self.num_envs
+        return E * chunk // n_chunks, E * (chunk + 1) // n_chunks
+
     # ---- state read-back / injection (synchronous; tests and the single-env shim) ----------------
     def get_maps(self, first=0, count=None):
         count = self.num_envs - first if count is None else count

@@ -157,16 +157,26 @@ class Agent(object):
             self.env.step_into(actions32, self.obs_buf[t + 1], self.rew_buf[t], self.done_buf[t])
         else:
             host['actions'].copy_(actions32)  # D2H, synchronous
-            self.env.step_host(host['actions'], host['obs'], host['reward'], host['done'])
-            if host['obs'].dtype == torch.uint8:
-                self.obs_buf[t + 1].copy_(host['obs'], non_blocking=True)
-            else:  # float32 on the host side (the reference's dtype): upload, then narrow on the device (lossless: values 0, 1, 2, 4)
-                if getattr(self, '_obs_f32', None) is None:
-                    self._obs_f32 = torch.empty(host['obs'].shape, dtype=torch.float32, device=self.device)
-                self._obs_f32.copy_(host['obs'], non_blocking=True)
-                self.obs_buf[t + 1].copy_(self._obs_f32)
-            self.rew_buf[t].copy_(host['reward'], non_blocking=True)
-            self.done_buf[t].copy_(host['done'], non_blocking=True)
+            # the host round trip of the reference's data flow (player_util.py:54-59), pipelined: the env's D2H of observation chunk c + 1
+            # (library stream) overlaps the policy-side H2D of chunk c (this stream); PCIe is full duplex
+            C_ = int(host.get('chunks', 8))
+            self.env.step_host_begin(host['actions'], host['obs'], host['reward'], host['done'], C_)
+            f32 = host['obs'].dtype != torch.uint8
+            if f32 and getattr(self, '_obs_f32', None) is None:
+                self._obs_f32 = torch.empty(host['obs'].shape, dtype=torch.float32, device=self.device)
+            for c in range(C_):
+                lo, hi = self.env.chunk_bounds(c, C_)
+                self.env.host_chunk_wait(c)
+                if c == 0:
+                    self.rew_buf[t].copy_(host['reward'], non_blocking=True)
+                    self.done_buf[t].copy_(host['done'], non_blocking=True)
+                if hi <= lo:
+                    continue
+                if f32:  # float32 on the host side (the reference's dtype): upload, then narrow on the device (lossless: values 0, 1, 2, 4)
+                    self._obs_f32[lo:hi].copy_(host['obs'][lo:hi], non_blocking=True)
+                    self.obs_buf[t + 1, lo:hi].copy_(self._obs_f32[lo:hi])
+                else:
+                    self.obs_buf[t + 1, lo:hi].copy_(host['obs'][lo:hi], non_blocking=True)
         eng.post_step(t, self.done_buf[t])
         self.reward = self.rew_buf[t]
         self.done = self.done_buf[t]

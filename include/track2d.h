@@ -133,6 +133,15 @@ int track2d_step_host(track2d_env *env, const int32_t *actions_host, float *obs_
 int track2d_reset_host_u8(track2d_env *env, const uint8_t *mask_host, uint8_t *obs_host);
 int track2d_step_host_u8(track2d_env *env, const int32_t *actions_host, uint8_t *obs_host, float *reward_host, uint8_t *done_host);
 
+/* The pipelined form of track2d_step_host[_u8]: same transition, but the observation D2H is issued as n_chunks (1..16) pieces of
+ * consecutive envs and the call returns after ENQUEUEING.  track2d_host_chunk_wait(env, c) blocks until chunk c -- envs
+ * [E c / n, E (c+1) / n) -- is in obs_host (reward_host / done_host are complete with chunk 0), so a consumer can process or re-upload
+ * chunk c while later chunks are still crossing the bus (PCIe is full duplex).  Host buffers should be pinned.  obs_host is float32
+ * (obs_is_u8 == 0, the reference's dtype, environment.py:146) or uint8. */
+int track2d_step_host_begin(track2d_env *env, const int32_t *actions_host, void *obs_host, int32_t obs_is_u8, float *reward_host,
+                            uint8_t *done_host, int32_t n_chunks);
+int track2d_host_chunk_wait(track2d_env *env, int32_t chunk);
+
 /* ---- state read-back / injection (host pointers, synchronous; parity tests and the gym shim) -- */
 
 /* maps as uint8 [count][H][W], 1 = wall (Track1v1Env.maze) */

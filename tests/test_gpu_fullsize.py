@@ -131,3 +131,32 @@ def test_cuda_astar_matches_reference_kats(t2d):
         assert int(g["replaces"][sel].sum()) == 0
         env.close()
     assert n_unsolvable >= 1
+
+
+@pytest.mark.parametrize("obs_dtype,n_chunks", [(torch.float32, 8), (torch.uint8, 3), (torch.float32, 16)])
+def test_pipelined_host_step_equals_host_step(t2d, obs_dtype, n_chunks):
+    """track2d_step_host_begin / track2d_host_chunk_wait (chunked, overlappable D2H) deliver exactly what track2d_step_host[_u8] does"""
+    E = 1003
+    a = t2d.Track2DVecEnv("Track2D-BlockPartialPZR-v0", num_envs=E, seed=9, rng="philox", auto_reset=True)
+    b = t2d.Track2DVecEnv("Track2D-BlockPartialPZR-v0", num_envs=E, seed=9, rng="philox", auto_reset=True)
+    ha, hb = a.alloc_host_buffers(obs_dtype=obs_dtype), b.alloc_host_buffers(obs_dtype=obs_dtype)
+    a.reset_host(ha["obs"])
+    b.reset_host(hb["obs"])
+    assert torch.equal(ha["obs"], hb["obs"])
+    rs = np.random.RandomState(2)
+    for t in range(30):
+        acts = torch.from_numpy(rs.randint(0, 4, size=(E, 2)).astype(np.int32))
+        ha["actions"].copy_(acts)
+        hb["actions"].copy_(acts)
+        a.step_host(ha["actions"], ha["obs"], ha["reward"], ha["done"])
+        hb["obs"].fill_(77)
+        b.step_host_begin(hb["actions"], hb["obs"], hb["reward"], hb["done"], n_chunks)
+        for c in range(n_chunks):
+            b.host_chunk_wait(c)
+            lo, hi = b.chunk_bounds(c, n_chunks)
+            assert torch.equal(hb["obs"][lo:hi], ha["obs"][lo:hi]), (t, c)
+            if c == 0:
+                assert torch.equal(hb["reward"], ha["reward"]) and torch.equal(hb["done"], ha["done"])
+    assert a.status() == 0 and b.status() == 0
+    a.close()
+    b.close()
