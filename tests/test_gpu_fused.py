@@ -222,7 +222,8 @@ def test_relu_backward_groupsum_matches_torch(lib, M, grouped):
 
 @pytest.mark.parametrize("N", [1, 9, 2051])
 def test_conv_stack_uint8_strided_matches_float32(lib, N):
-    """the image-source variants of the conv stack (uint8 / strided) give the float32 / packed results bit for bit"""
+    """the image-source variants of the conv stack: uint8 / strided images run conv2 on the tensor cores (3xTF32, track2d_conv_tc.cu), float32 /
+    packed images on the FP32 CUDA-core kernels (track2d_policy.cu) -- same results to float32 accuracy"""
     from active_tracking_rl_b200 import _lib
     g = torch.Generator(device=DEV).manual_seed(N)
     obs = torch.tensor([0, 1, 2, 4], device=DEV, dtype=torch.uint8)[torch.randint(0, 4, (N, 2, 169), generator=g, device=DEV)]
@@ -234,15 +235,15 @@ def test_conv_stack_uint8_strided_matches_float32(lib, N):
         y_ref, y_got = torch.zeros(N, 512, device=DEV), torch.zeros(N, 512, device=DEV)
         _lib.check(lib.track2d_maze_conv_forward(_p(xf), N, _p(w1), _p(b1), _p(w2), _p(b2), _p(y_ref), _stream()), lib)
         _lib.check(lib.track2d_maze_conv_forward_ex(C.c_void_p(obs.data_ptr() + 169 * agent), 1, 338, N, _p(w1), _p(b1), _p(w2), _p(b2), _p(y_got), _stream()), lib)
-        assert torch.equal(y_ref, y_got)
-        if N == 9:  # a single CTA: the accumulation order is fixed, so the gradients are bit-identical too
+        assert torch.allclose(y_ref, y_got, rtol=3e-5, atol=3e-5), (y_ref - y_got).abs().max()
+        if N in (9, 2051):
             gr = [torch.zeros_like(t) for t in (w1, b1, w2, b2)]
             gg = [torch.zeros_like(t) for t in (w1, b1, w2, b2)]
             _lib.check(lib.track2d_maze_conv_backward(_p(xf), _p(y_ref), _p(gy), N, _p(w1), _p(b1), _p(w2), *[_p(t) for t in gr], _stream()), lib)
             _lib.check(lib.track2d_maze_conv_backward_ex(C.c_void_p(obs.data_ptr() + 169 * agent), 1, 338, _p(y_ref), _p(gy), N, _p(w1), _p(b1), _p(w2),
                                                          *[_p(t) for t in gg], _stream()), lib)
             for a, b in zip(gr, gg):
-                assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)
+                assert float((a - b).abs().max()) <= 1e-4 * float(a.abs().max()) + 1e-6, (float((a - b).abs().max()), float(a.abs().max()))
 
 
 @pytest.mark.parametrize("env_id,network,aux,mode,E", [("Track2D-BlockPartialPZR-v0", "tat-maze-lstm", "reward", -1, 64),
