@@ -13,6 +13,7 @@ TARGET = {"Adv": 0, "PZR": 1, "Far": 2, "Nav": 3, "Ram": 4, "RPF": 5}
 RNG = {"philox": 0, "numpy": 1}
 FLAG_AUTO_RESET = 1
 FLAG_KEEP_F64 = 2
+FLAG_PLAN_AHEAD = 4
 STATUS_BAD_ACTION, STATUS_PLAN_OVERFLOW, STATUS_ASTAR_REPLACE, STATUS_HEAP_OVERFLOW = 1, 2, 4, 8
 NAV_MAXPLAN = 1024
 RAM_MAXPLAN = 9
@@ -50,6 +51,7 @@ SYMBOLS = {
     "track2d_step_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "track2d_reset_host_u8": (C.c_int, [_vp, _vp, _vp]),
     "track2d_step_host_u8": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "track2d_join": (C.c_int, [_vp, _vp]),
     "track2d_step_host_begin": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp, _i32]),
     "track2d_host_chunk_wait": (C.c_int, [_vp, _i32]),
     "track2d_get_maps": (C.c_int, [_vp, _i32, _i32, _vp]),

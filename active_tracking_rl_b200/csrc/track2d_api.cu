@@ -20,6 +20,10 @@ cudaError_t t2d_launch_reset_u8(const World &w, const uint8_t *mask, int from_li
 cudaError_t t2d_launch_seed_numpy(const World &w, int first, int count, unsigned long long seed, int add_index, cudaStream_t s);
 cudaError_t t2d_launch_nav_replan(const World &w, cudaStream_t s);
 cudaError_t t2d_launch_astar_direct(const World &w, int first, int count, const int32_t *sg_dev, int32_t *len_dev, cudaStream_t s);
+cudaError_t t2d_launch_nav_fill(const World &w, const uint8_t *mask, const uint32_t *list, const uint32_t *count, cudaStream_t s);
+cudaError_t t2d_launch_nav_ahead(const World &w, uint32_t *list, uint32_t *count, cudaStream_t s);
+cudaError_t t2d_launch_nav_merge(const World &w, cudaStream_t s);
+cudaError_t t2d_launch_swap_standby(const World &w, const World &sw, void *obs, int obs_u8, uint32_t *regen_list, uint32_t *regen_count, cudaStream_t s);
 int t2d_nav_slots();
 
 static thread_local char g_err[512] = "";
@@ -46,6 +50,14 @@ struct track2d_env {
     uint8_t *d_mask;
     cudaEvent_t chunk_ev[16];  // track2d_step_host_begin: one event per observation chunk
     int n_chunk_ev;
+    // standby worlds / plan-ahead (Philox, auto-reset; Nav targets and Maze maps): see track2d_reset.cu
+    bool standby;              // auto-reset = copy of a world prepared ahead on the side stream
+    World sw;                  // the standby world (same layout, its own arrays)
+    cudaStream_t side;
+    cudaEvent_t ev_main[8], ev_side[8];
+    unsigned since_join;       // steps issued since the side stream was last joined
+    uint32_t *regen_lists, *regen_counts, *ahead_list, *ahead_count;
+    uint8_t *side_ws;
     bool was_reset;
     unsigned long long steps_done;
     std::vector<void *> allocs;
@@ -116,6 +128,14 @@ int do_reset(track2d_env *env, const uint8_t *mask, ObsT *obs, int init_only, cu
         else err = t2d_launch_full_obs_u8(w, (uint8_t *)obs, mask, s);
         T2D_CUDA(err);
     }
+    if (!init_only && env->standby) {
+        // live look-ahead, then the standby worlds of the envs that were just reset (rare: done on the caller's stream)
+        if (w.async_nav) T2D_CUDA(t2d_launch_nav_fill(w, mask, nullptr, nullptr, s));
+        T2D_CUDA(cudaMemcpyAsync(env->sw.episode, w.episode, (size_t)w.E * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+        T2D_CUDA(t2d_launch_reset_u8(env->sw, mask, 0, nullptr, 0, s));
+        if (w.async_nav) T2D_CUDA(t2d_launch_nav_fill(env->sw, mask, nullptr, nullptr, s));
+        t2d_count_launches(w.async_nav ? 3 : 1);
+    }
     if (!init_only) env->was_reset = true;
     return T2D_OK;
 }
@@ -131,6 +151,41 @@ int do_step(track2d_env *env, const int32_t *actions, ObsT *obs, float *reward, 
     T2D_REQUIRE(obs == nullptr || ((uintptr_t)obs & 15u) == 0, "step: obs buffer must be 16-byte aligned");
     T2D_REQUIRE(((uintptr_t)actions & 7u) == 0 && ((uintptr_t)reward & 7u) == 0, "step: actions/reward buffers must be 8-byte aligned");
     cudaError_t err;
+    if (env->standby) {
+        constexpr unsigned R = 8, LAG = 4;
+        const unsigned j = env->since_join, slot = j % R;
+        if (j >= LAG) T2D_CUDA(cudaStreamWaitEvent(s, env->ev_side[(j - LAG) % R], 0));  // side work issued LAG steps ago is done
+        if (w.async_nav) {
+            T2D_CUDA(t2d_launch_nav_merge(w, s));  // hand-over of finished segments + the synchronous fallback for a starved target
+            t2d_count_launches(4);
+        }
+        if (sizeof(ObsT) == 4) err = t2d_launch_step_f32(w, actions, (float *)obs, reward, done, s);
+        else err = t2d_launch_step_u8(w, actions, (uint8_t *)obs, reward, done, s);
+        T2D_CUDA(err);
+        uint32_t *rl = env->regen_lists + (size_t)slot * w.E, *rc4 = env->regen_counts + slot * 4;
+        T2D_CUDA(cudaMemsetAsync(rc4, 0, 4 * sizeof(uint32_t), s));
+        T2D_CUDA(t2d_launch_swap_standby(w, env->sw, obs, sizeof(ObsT) == 1, rl, rc4, s));
+        t2d_count_launches(2);
+        // side stream: new standby worlds for the envs that were just swapped in, then plan ahead on the live world
+        T2D_CUDA(cudaEventRecord(env->ev_main[slot], s));
+        T2D_CUDA(cudaStreamWaitEvent(env->side, env->ev_main[slot], 0));
+        World sws = env->sw;
+        sws.work_list = rl;
+        sws.work_count = rc4;
+        T2D_CUDA(t2d_launch_reset_u8(sws, nullptr, 1, nullptr, 0, env->side));
+        t2d_count_launches(1);
+        if (w.async_nav) {
+            T2D_CUDA(t2d_launch_nav_fill(sws, nullptr, rl, rc4 + 3, env->side));
+            World wl = w;
+            wl.astar_ws = env->side_ws;
+            T2D_CUDA(t2d_launch_nav_ahead(wl, env->ahead_list, env->ahead_count, env->side));
+            t2d_count_launches(3);
+        }
+        T2D_CUDA(cudaEventRecord(env->ev_side[slot], env->side));
+        env->since_join = j + 1;
+        env->steps_done += (unsigned long long)w.E;
+        return T2D_OK;
+    }
     T2D_CUDA(t2d_launch_nav_replan(w, s));
     if (w.target_mode == T2D_TARGET_NAV || w.target_mode == T2D_TARGET_RPF) t2d_count_launches(3);
     if (sizeof(ObsT) == 4) err = t2d_launch_step_f32(w, actions, (float *)obs, reward, done, s);
@@ -237,7 +292,54 @@ int track2d_create(const track2d_config *cfg, track2d_env **out) {
         ALLOC(w.mt_pos, E);
     }
     if (cfg->flags & T2D_FLAG_KEEP_F64) ALLOC(w.rew64, 2 * (size_t)E);
+    // Opt-in (T2D_FLAG_PLAN_AHEAD): auto-resets as copies of worlds prepared ahead of time, Nav plans made ahead of time.  The RNG is
+    // counter-based, so WHEN something is computed cannot change WHAT comes out.
+    env->standby = cfg->rng_mode == T2D_RNG_PHILOX && (cfg->flags & T2D_FLAG_AUTO_RESET) && (cfg->flags & T2D_FLAG_PLAN_AHEAD) &&
+                   cfg->obs_type == T2D_OBS_PARTIAL && (cfg->target_mode == T2D_TARGET_NAV || (cfg->map_type == T2D_MAP_MAZE && cfg->target_mode != T2D_TARGET_RPF));
+    if (env->standby) {
+        w.async_nav = cfg->target_mode == T2D_TARGET_NAV;
+        World &sw = env->sw;
+        sw = w;
+        ALLOC(sw.maps, (size_t)E * T2D_MAP_WORDS);
+        ALLOC(sw.pos, E);
+        ALLOC(sw.ctr, E);
+        ALLOC(sw.goals, E);
+        ALLOC(sw.ram, E);
+        ALLOC(sw.episode, E);
+        ALLOC(sw.rpf, E);
+        ALLOC(sw.status, 1);
+        ALLOC(sw.stats, 2);
+        ALLOC(sw.nav_meta, E);
+        ALLOC(sw.nav_goal, E);
+        ALLOC(env->regen_lists, 8 * (size_t)E);
+        ALLOC(env->regen_counts, 8 * 4);
+        if (w.async_nav) {
+            ALLOC(w.nav_end, E);
+            ALLOC(w.ext_info, E);
+            ALLOC(w.ext_plan, (size_t)E * T2D_NAV_PLAN_BYTES);
+            ALLOC(sw.nav_plan, (size_t)E * T2D_NAV_PLAN_BYTES);
+            ALLOC(sw.nav_end, E);
+            ALLOC(env->side_ws, (size_t)w.astar_slots * (82 * 82) * 16);
+            ALLOC(env->ahead_list, E);
+            ALLOC(env->ahead_count, 4);
+            sw.astar_ws = env->side_ws;
+            sw.ext_info = nullptr;
+            sw.ext_plan = nullptr;
+        }
+        sw.rew64 = nullptr;
+        sw.flags = cfg->flags;
+    }
 #undef ALLOC
+    if (rc == T2D_OK && env->standby) {
+        bool ok = cudaStreamCreateWithFlags(&env->side, cudaStreamNonBlocking) == cudaSuccess;
+        for (int i = 0; i < 8 && ok; i++)
+            ok = cudaEventCreateWithFlags(&env->ev_main[i], cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&env->ev_side[i], cudaEventDisableTiming) == cudaSuccess;
+        if (!ok) {
+            t2d_set_error("create: side stream / events: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = T2D_E_CUDA;
+        }
+    }
     if (rc == T2D_OK && cudaStreamCreateWithFlags(&env->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
         t2d_set_error("create: cudaStreamCreate failed");
         rc = T2D_E_CUDA;
@@ -264,6 +366,13 @@ int track2d_destroy(track2d_env *env) {
     cudaDeviceSynchronize();
     for (void *p : env->allocs) cudaFree(p);
     for (int c = 0; c < env->n_chunk_ev; c++) cudaEventDestroy(env->chunk_ev[c]);
+    if (env->standby) {
+        for (int i = 0; i < 8; i++) {
+            if (env->ev_main[i]) cudaEventDestroy(env->ev_main[i]);
+            if (env->ev_side[i]) cudaEventDestroy(env->ev_side[i]);
+        }
+        if (env->side) cudaStreamDestroy(env->side);
+    }
     if (env->own_stream) cudaStreamDestroy(env->own_stream);
     delete env;
     return T2D_OK;
@@ -403,6 +512,15 @@ int track2d_step_host_u8(track2d_env *env, const int32_t *actions_host, uint8_t 
     T2D_REQUIRE(actions_host, "step_host_u8: actions required");
     DeviceGuard guard(env->cfg.device);
     return step_host_t<uint8_t>(env, actions_host, obs_host, reward_host, done_host);
+}
+
+int track2d_join(track2d_env *env, void *stream) {
+    T2D_REQUIRE(env, "null handle");
+    if (!env->standby || env->since_join == 0) return T2D_OK;
+    DeviceGuard guard(env->cfg.device);
+    T2D_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, env->ev_side[(env->since_join - 1) % 8], 0));
+    env->since_join = 0;
+    return T2D_OK;
 }
 
 int track2d_step_host_begin(track2d_env *env, const int32_t *actions_host, void *obs_host, int32_t obs_is_u8, float *reward_host, uint8_t *done_host,
@@ -547,11 +665,15 @@ int track2d_get_nav(track2d_env *env, int32_t first, int32_t count, int32_t *pla
     T2D_CUDA(cudaMemcpy(meta.data(), env->w.nav_meta + first, (size_t)count * 4, cudaMemcpyDeviceToHost));
     T2D_CUDA(cudaMemcpy(goal.data(), env->w.nav_goal + first, (size_t)count * 4, cudaMemcpyDeviceToHost));
     for (int i = 0; i < count; i++) {
+        // plan-ahead handles keep the plan as a ring whose length and cursor only grow: report it re-based at the cursor
+        const int shift = env->w.async_nav ? (int)(meta[i] >> 16) : 0;
         if (plan_host)
-            for (int k = 0; k < TRACK2D_NAV_MAXPLAN; k++)
-                plan_host[(size_t)TRACK2D_NAV_MAXPLAN * i + k] = (plan[(size_t)i * T2D_NAV_PLAN_BYTES + (k >> 2)] >> (2 * (k & 3))) & 3;
-        len_host[i] = meta[i] & 0xFFFF;
-        idx_host[i] = meta[i] >> 16;
+            for (int k = 0; k < TRACK2D_NAV_MAXPLAN; k++) {
+                const int q = (k + shift) & (TRACK2D_NAV_MAXPLAN - 1);
+                plan_host[(size_t)TRACK2D_NAV_MAXPLAN * i + k] = (plan[(size_t)i * T2D_NAV_PLAN_BYTES + (q >> 2)] >> (2 * (q & 3))) & 3;
+            }
+        len_host[i] = (int)((meta[i] & 0xFFFF) - (uint32_t)shift) & 0xFFFF;
+        idx_host[i] = (int)(meta[i] >> 16) - shift;
         if (goal_host) { goal_host[2 * i] = goal[i] & 255; goal_host[2 * i + 1] = (goal[i] >> 8) & 255; }
     }
     return T2D_OK;
@@ -561,6 +683,10 @@ int track2d_set_nav(track2d_env *env, int32_t first, int32_t count, const int32_
     int rc = check_range(env, first, count);
     if (rc != T2D_OK) return rc;
     T2D_REQUIRE(env->w.nav_plan, "set_nav: not a Nav/RPF env");
+    if (env->w.async_nav) {
+        t2d_set_error("set_nav: this handle plans ahead of time (Philox + auto-reset); create it without T2D_FLAG_PLAN_AHEAD to inject plans");
+        return T2D_E_UNSUPPORTED;
+    }
     DeviceGuard guard(env->cfg.device);
     T2D_CUDA(cudaDeviceSynchronize());
     std::vector<uint8_t> plan((size_t)count * T2D_NAV_PLAN_BYTES, 0);

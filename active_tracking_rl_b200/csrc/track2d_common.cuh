@@ -51,6 +51,12 @@ struct World {
     unsigned long long *stats; // [2] episodes finished, env-steps done
     uint8_t *astar_ws;   // A* workspace (Nav/RPF only)
     int astar_slots;
+    // ---- asynchronous planning (Philox + Nav + auto-reset; see track2d_reset.cu "plan-ahead") -------------------------------
+    int async_nav;       // 1: nav_plan is an append-only ring (len and idx of nav_meta only grow), fed ahead of time
+    uint32_t *nav_end;   // [E] cell the target stands on after the last planned action (row | col << 8)
+    uint4 *ext_info;     // [E] hand-over slot of the side-stream planner: x = state (0 idle, 2 planning, 1 ready) | episode << 8,
+                         //     y = base | length << 16, z = goal, w = end cell
+    uint8_t *ext_plan;   // [E][T2D_NAV_PLAN_BYTES] the planned segment, slots 0 .. length-1
 };
 
 // ---- map bit helpers ---------------------------------------------------------------------------

@@ -14,7 +14,7 @@
 #pragma once
 #include "track2d_common.cuh"
 
-#define T2D_HEAP_SMEM 1024
+#define T2D_HEAP_SMEM 320
 #define T2D_MAX_CELLS (82 * 82)
 
 struct __align__(16) HeapEntry {  // one 16-byte shared-memory access per heap slot
@@ -24,9 +24,9 @@ struct __align__(16) HeapEntry {  // one 16-byte shared-memory access per heap s
 };
 
 struct AStarScratch {
-    uint16_t gcost[T2D_MAX_CELLS]; // 0xFFFF = never seen; bit 15 = explored; low 15 bits = path cost
-    uint8_t pact[T2D_MAX_CELLS];   // action that led into the cell
+    uint16_t gcost[T2D_MAX_CELLS]; // 0xFFFF = never seen; bit 15 = explored; bits 13-14 = action that led into the cell; low 13 bits = path cost
     HeapEntry heap[T2D_HEAP_SMEM]; // the first T2D_HEAP_SMEM slots of the frontier (frontiers of real maps stay below ~250)
+    // 19.7 KB per plan: eleven one-warp planners per SM (the planner is latency-bound on one lane: throughput = plans in flight)
 };
 
 // FAST: every index touched is < T2D_HEAP_SMEM (checked once per heap operation by the caller), so the accesses are plain
@@ -95,13 +95,26 @@ __device__ __forceinline__ uint32_t rpf_corner(int H, int W, int q) { // generat
 // Astar_solver.py:121-149 on the bit grid `bm` (generator maze), one warp per plan.  The frontier is CPython's heapq replayed
 // array operation by array operation on lane 0 (that fixes WHICH shortest path comes out); lanes 0..3 expand the four
 // neighbours of the popped node in parallel (wall bit, seen / explored lookup, f = g + float64 euclidean distance), and lane 0
-// pushes the new ones in action order.  Writes the action list (get_actions, :102-110) 2 bits per action into w.nav_plan[e] and
-// returns its length, or -1 when the goal is unreachable.  start/goal are (row, col) map coordinates.
-__device__ int astar_plan(const World &w, int e, const uint32_t *bm, AStarScratch &a, int slot, int sr, int sc, int gr, int gc, int lane) {
+// pushes the new ones in action order.  Writes the action list (get_actions, :102-110) 2 bits per action into `plan` (a buffer of
+// TRACK2D_NAV_MAXPLAN 2-bit slots, used as a ring) starting at slot `base`, and returns its length, or -1 when the goal is
+// unreachable.  base < 0: the buffer is cleared first and the plan starts at slot 0 (the reference's "new plan replaces the old one").
+// start/goal are (row, col) map coordinates.
+__device__ __forceinline__ void plan_put(uint8_t *plan, int slot, int act) {
+    slot &= TRACK2D_NAV_MAXPLAN - 1;
+    const int sh = 2 * (slot & 3);
+    plan[slot >> 2] = (uint8_t)((plan[slot >> 2] & ~(3 << sh)) | (act << sh));
+}
+__device__ __forceinline__ int plan_get(const uint8_t *plan, int slot) {
+    slot &= TRACK2D_NAV_MAXPLAN - 1;
+    return (plan[slot >> 2] >> (2 * (slot & 3))) & 3;
+}
+__device__ int astar_plan(const World &w, uint8_t *plan, int base, const uint32_t *bm, AStarScratch &a, int slot, int sr, int sc, int gr, int gc, int lane) {
     const int W = w.W, cells = w.H * w.W;
     for (int i = lane; i < cells; i += 32) a.gcost[i] = 0xFFFFu;
-    uint8_t *plan = w.nav_plan + (size_t)e * T2D_NAV_PLAN_BYTES;
-    for (int i = lane; i < T2D_NAV_PLAN_BYTES; i += 32) plan[i] = 0;
+    if (base < 0) {
+        for (int i = lane; i < T2D_NAV_PLAN_BYTES; i += 32) plan[i] = 0;
+        base = 0;
+    }
     __syncwarp();
     HeapEntry *spill = reinterpret_cast<HeapEntry *>(w.astar_ws + (size_t)slot * T2D_MAX_CELLS * sizeof(HeapEntry));
     const HeapView<true> hfast{a.heap, spill};
@@ -153,12 +166,11 @@ __device__ int astar_plan(const World &w, int e, const uint32_t *bm, AStarScratc
                 const int child = nr * W + nc;
                 const uint32_t gv = a.gcost[child];
                 if (gv == 0xFFFFu) {
-                    a.gcost[child] = (uint16_t)(g + 1);
-                    a.pact[child] = (uint8_t)lane;
+                    a.gcost[child] = (uint16_t)((g + 1) | (lane << 13));
                     const double dr = (double)(nr - gr), dc = (double)(nc - gc);
                     f = __dadd_rn((double)(g + 1), __dsqrt_rn(__dadd_rn(__dmul_rn(dr, dr), __dmul_rn(dc, dc))));
                     add = true;
-                } else if (!(gv & 0x8000u) && (int)(gv & 0x7FFFu) < g + 1) {
+                } else if (!(gv & 0x8000u) && (int)(gv & 0x1FFFu) < g + 1) {
                     atomicOr(w.status, (uint32_t)T2D_STATUS_ASTAR_REPLACE);
                 }
             }
@@ -184,12 +196,12 @@ __device__ int astar_plan(const World &w, int e, const uint32_t *bm, AStarScratc
     }
     int len = -1;
     if (lane == 0 && sol >= 0) {
-        len = a.gcost[sol] & 0x7FFF;
+        len = a.gcost[sol] & 0x1FFF;
         if (len > TRACK2D_NAV_MAXPLAN) atomicOr(w.status, (uint32_t)T2D_STATUS_PLAN_OVERFLOW);
         int cell = sol;
         for (int i = len - 1; i >= 0; i--) {
-            int act = a.pact[cell];
-            if (i < TRACK2D_NAV_MAXPLAN) plan[i >> 2] |= (uint8_t)(act << (2 * (i & 3)));
+            int act = (a.gcost[cell] >> 13) & 3;
+            if (i < TRACK2D_NAV_MAXPLAN) plan_put(plan, base + i, act);
             cell -= action_dr(act) * W + action_dc(act);
         }
         if (len > TRACK2D_NAV_MAXPLAN) len = TRACK2D_NAV_MAXPLAN;
@@ -199,9 +211,7 @@ __device__ int astar_plan(const World &w, int e, const uint32_t *bm, AStarScratc
     return len;
 }
 
-__device__ __forceinline__ void nav_store_planb(const World &w, int e, const uint32_t acts[10]) {
-    uint8_t *plan = w.nav_plan + (size_t)e * T2D_NAV_PLAN_BYTES;
-    plan[0] = (uint8_t)(acts[0] | (acts[1] << 2) | (acts[2] << 4) | (acts[3] << 6));
-    plan[1] = (uint8_t)(acts[4] | (acts[5] << 2) | (acts[6] << 4) | (acts[7] << 6));
-    plan[2] = (uint8_t)(acts[8] | (acts[9] << 2));
+__device__ __forceinline__ void nav_store_planb(uint8_t *plan, int base, const uint32_t acts[10]) {
+    if (base < 0) base = 0;
+    for (int i = 0; i < 10; i++) plan_put(plan, base + i, (int)acts[i]);
 }

@@ -294,22 +294,29 @@ struct PhiloxNavPolicy {
 // Shared tail of Navigator.reset (navigator.py:38-63) and of the replan inside Navigator.step (:15-36):
 // A* to `goal`; while unsolvable or empty: up to 5 fresh goals; then plan B = 10 random actions.
 template <typename Policy>
-__device__ void nav_plan_from(const World &w, int e, Policy &P, int slot, int sr, int sc, uint32_t goal, int lane) {
+__device__ int nav_plan_into(const World &w, uint8_t *plan, int base, Policy &P, int slot, int sr, int sc, uint32_t &goal, int lane) {
     int count_res = 0;
     bool planb = false;
-    int len = astar_plan(w, e, P.bm(), P.astar(), slot, sr, sc, (int)(goal & 255u), (int)((goal >> 8) & 255u), lane);
+    int len = astar_plan(w, plan, base, P.bm(), P.astar(), slot, sr, sc, (int)(goal & 255u), (int)((goal >> 8) & 255u), lane);
     while (len < 1) {
         count_res++;
         if (count_res > 5) { planb = true; break; }
         goal = P.sample_goal1(lane);
-        len = astar_plan(w, e, P.bm(), P.astar(), slot, sr, sc, (int)(goal & 255u), (int)((goal >> 8) & 255u), lane);
+        len = astar_plan(w, plan, base, P.bm(), P.astar(), slot, sr, sc, (int)(goal & 255u), (int)((goal >> 8) & 255u), lane);
     }
     if (planb) {
         uint32_t acts[10];
         P.plan_b(acts, lane);
-        if (lane == 0) nav_store_planb(w, e, acts);
+        if (lane == 0) nav_store_planb(plan, base, acts);
         len = 10;
     }
+    __syncwarp();
+    return len;
+}
+// the reference's semantics: the new plan REPLACES the old one (a_i = 0)
+template <typename Policy>
+__device__ void nav_plan_from(const World &w, int e, Policy &P, int slot, int sr, int sc, uint32_t goal, int lane) {
+    const int len = nav_plan_into(w, w.nav_plan + (size_t)e * T2D_NAV_PLAN_BYTES, -1, P, slot, sr, sc, goal, lane);
     if (lane == 0) {
         w.nav_meta[e] = (uint32_t)len; // a_i = 0
         w.nav_goal[e] = goal & 0xFFFFu;
@@ -317,11 +324,21 @@ __device__ void nav_plan_from(const World &w, int e, Policy &P, int slot, int sr
     __syncwarp();
 }
 
+// the cell an agent ends on after `len` planned actions from (r, c) under the env's move rule (track_1v1.py:271-285: a wall blocks)
+__device__ uint32_t plan_end_cell(const uint32_t *bm, const uint8_t *plan, int base, int len, int r, int c) {
+    for (int i = 0; i < len; i++) {
+        const int a = plan_get(plan, base + i);
+        const int nr = r + action_dr(a), nc = c + action_dc(a);
+        if (!((bm[map_word_index(nr, nc)] >> ((nc + T2D_PAD) & 31)) & 1u)) { r = nr; c = nc; }
+    }
+    return (uint32_t)r | ((uint32_t)c << 8);
+}
+
 // ---- Philox reset ----------------------------------------------------------------------------------
 // `nav` is non-NULL only for the Nav / RPF instantiation (it then also provides bm).
 template <typename ObsT, int MAP>
 __device__ __noinline__ void reset_env_philox(const World &w, int e, uint32_t *bm, uint32_t *walkw, PhiloxNavScratch *nav, int slot, ObsT *obs, int lane,
-                                              bool init_only) {
+                                              bool init_only, bool defer_plan = false) {
     const uint32_t episode = w.episode[e];
     Philox rng; // stream 0: the same on every lane (scalar decisions need no shuffles)
     rng.init(w.seed, (uint32_t)e, episode, 0u);
@@ -459,11 +476,20 @@ __device__ __noinline__ void reset_env_philox(const World &w, int e, uint32_t *b
             uint32_t word = ram_new_plan(rng, false, 0); // RamAgent.reset (navigator.py:90-93)
             if (lane == 0) w.ram[e] = word;
         }
-        if (nav) {
+        if (nav && defer_plan) {
+            // auto-reset inside step(): the first plan is left to the replan wave at the start of the NEXT step (same Philox stream, same
+            // goal, same start cell -> the same plan), so a step waits for ONE wave of A* plans instead of two
+            if (lane == 0) {
+                w.nav_meta[e] = 0u;  // length 0, cursor 0: "exhausted"
+                w.nav_goal[e] = (goals >> 16) & 0xFFFFu;
+            }
+        } else if (nav) {
             Philox nrng;
             nrng.init(w.seed, (uint32_t)e, episode, 3u);
             PhiloxNavPolicy P{w, e, *nav, nrng};
             nav_plan_from(w, e, P, slot, r1, c1, goals >> 16, lane); // Navigator.reset(init_states[1], goal_states[1])
+            if (w.async_nav && lane == 0)
+                w.nav_end[e] = plan_end_cell(bm, w.nav_plan + (size_t)e * T2D_NAV_PLAN_BYTES, 0, (int)(w.nav_meta[e] & 0xFFFFu), r1, c1);
         }
         if (lane == 0) {
             w.ctr[e] = 0;
@@ -508,7 +534,7 @@ __global__ void __launch_bounds__(32) reset_philox_nav_kernel(World w, const uin
         int e = i;
         if (from_list) e = (int)w.work_list[i];
         else if (mask && !mask[e]) continue;
-        reset_env_philox<ObsT, MAP>(w, e, s.bm, walkw, &s, blockIdx.x, obs, lane, init_only != 0);
+        reset_env_philox<ObsT, MAP>(w, e, s.bm, walkw, &s, blockIdx.x, obs, lane, init_only != 0, from_list && !w.async_nav);
         __syncwarp();
     }
     if (from_list) finish_reset(w);
@@ -683,13 +709,22 @@ __global__ void __launch_bounds__(32) nav_replan_philox_kernel(World w) {
     const int n = (int)w.work_count[1];
     for (int i = blockIdx.x; i < n; i += gridDim.x) {
         const int e = (int)w.work_list[w.E + i];
-        Philox rng;
-        rng.init(w.seed, (uint32_t)e, w.episode[e], 0x20000u + (w.ctr[e] >> 16));
+        const uint32_t elapsed = w.ctr[e] >> 16, p = w.pos[e];
         load_gen_maze(w, e, s.bm, lane);
-        PhiloxNavPolicy P{w, e, s, rng};
-        uint32_t goal = P.sample_goal1(lane);
-        uint32_t p = w.pos[e];
-        nav_plan_from(w, e, P, blockIdx.x, (int)(p >> 16) & 255, (int)(p >> 24), goal, lane);
+        Philox rng;
+        if (elapsed == 0u && w.nav_meta[e] == 0u) {
+            // the first plan of an episode the last auto-reset started: Navigator.reset(init_states[1], goal_states[1]) with the stream
+            // and the goal the reset kernel would have used
+            const uint32_t goal = w.nav_goal[e];
+            rng.init(w.seed, (uint32_t)e, w.episode[e] - 1u, 3u);
+            PhiloxNavPolicy P{w, e, s, rng};
+            nav_plan_from(w, e, P, blockIdx.x, (int)(p >> 16) & 255, (int)(p >> 24), goal, lane);
+        } else {
+            rng.init(w.seed, (uint32_t)e, w.episode[e], 0x20000u + elapsed);
+            PhiloxNavPolicy P{w, e, s, rng};
+            const uint32_t goal = P.sample_goal1(lane);
+            nav_plan_from(w, e, P, blockIdx.x, (int)(p >> 16) & 255, (int)(p >> 24), goal, lane);
+        }
         __syncwarp();
     }
 }
@@ -702,11 +737,213 @@ __global__ void __launch_bounds__(32) astar_direct_kernel(World w, int first, in
     for (int i = blockIdx.x; i < count; i += gridDim.x) {
         const int e = first + i;
         load_gen_maze(w, e, s.bm, lane);
-        const int len = astar_plan(w, e, s.bm, s.astar, blockIdx.x, sg[4 * i], sg[4 * i + 1], sg[4 * i + 2], sg[4 * i + 3], lane);
+        const int len = astar_plan(w, w.nav_plan + (size_t)e * T2D_NAV_PLAN_BYTES, -1, s.bm, s.astar, blockIdx.x, sg[4 * i], sg[4 * i + 1], sg[4 * i + 2], sg[4 * i + 3], lane);
         if (lane == 0) {
             len_out[i] = len;
             w.nav_meta[e] = (uint32_t)(len > 0 ? len : 0);
             w.nav_goal[e] = (uint32_t)sg[4 * i + 2] | ((uint32_t)sg[4 * i + 3] << 8);
+        }
+        __syncwarp();
+    }
+}
+
+// =====================================================================================================================
+// Plan-ahead (Philox + Nav + auto-reset).  A scripted Nav target never reacts to the tracker, so its whole trajectory is a function
+// of (seed, env, episode): plan k of an episode starts where plan k-1 ends and draws its goal from Philox(seed, env, episode,
+// 0x20000 + first step of the plan) -- exactly the key the synchronous replan uses when the plan runs out.  So plans can be made
+// BEFORE they are needed: nav_plan becomes an append-only ring (length and cursor of nav_meta only grow), a planner on a side stream
+// keeps ~NAV_LOW actions ahead of every target and hands segments over through ext_info / ext_plan, the main stream merges them
+// between steps; next-episode worlds ("standby": map, spawn, goals, first plans) are prepared on the side stream too, so that an
+// auto-reset is a copy.  The synchronous replan stays as the fallback for a starved env; results do not depend on the timing.
+constexpr int NAV_LOW = 24;   // the side-stream planner extends a plan once fewer than this many actions lie ahead of the target
+constexpr int NAV_MIN = 12;   // a freshly reset world starts with at least this many (the planner's hand-over lags a few steps)
+
+// one more segment for env e of world w, planned from cell `start` at absolute step `base_abs`, written to out[out_base ...)
+__device__ int plan_segment(const World &w, int e, uint32_t episode, int base_abs, uint32_t start, uint8_t *out, int out_base, PhiloxNavScratch &s, int slot,
+                            int lane, uint32_t &goal, uint32_t &end) {
+    Philox rng;
+    rng.init(w.seed, (uint32_t)e, episode, 0x20000u + (uint32_t)base_abs);
+    PhiloxNavPolicy P{w, e, s, rng};
+    goal = P.sample_goal1(lane);  // self.goal_states = maze_generator.sample_goal(1)[0]
+    const int len = nav_plan_into(w, out, out_base, P, slot, (int)(start & 255u), (int)((start >> 8) & 255u), goal, lane);
+    uint32_t en = 0;
+    if (lane == 0) en = plan_end_cell(s.bm, out, out_base, len, (int)(start & 255u), (int)((start >> 8) & 255u));
+    end = __shfl_sync(0xFFFFFFFFu, en, 0);
+    return len;
+}
+
+// direct mode: extend the plan of every listed (or masked) env until NAV_MIN actions lie ahead.  Used where nothing else touches the
+// world: on the live world right after a full reset (main stream) and on the standby world (side stream).
+__global__ void __launch_bounds__(32) nav_fill_kernel(World w, const uint8_t *__restrict__ mask, const uint32_t *__restrict__ list, const uint32_t *__restrict__ count) {
+    __shared__ PhiloxNavScratch s;
+    const int lane = threadIdx.x;
+    const int n = list ? (int)*count : w.E;
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        int e = i;
+        if (list) e = (int)list[i];
+        else if (mask && !mask[e]) continue;
+        load_gen_maze(w, e, s.bm, lane);
+        uint32_t meta = w.nav_meta[e], end = w.nav_end[e];
+        const uint32_t episode = w.episode[e];  // (the value the synchronous replan keys on: already advanced by the reset)
+        uint8_t *plan = w.nav_plan + (size_t)e * T2D_NAV_PLAN_BYTES;
+        while ((int)((meta & 0xFFFFu) - (meta >> 16)) < NAV_MIN) {
+            uint32_t goal;
+            const int len = plan_segment(w, e, episode, (int)(meta & 0xFFFFu), end, plan, (int)(meta & 0xFFFFu), s, blockIdx.x, lane, goal, end);
+            meta += (uint32_t)len;
+            if (lane == 0) w.nav_goal[e] = goal & 0xFFFFu;
+        }
+        if (lane == 0) {
+            w.nav_meta[e] = meta;
+            w.nav_end[e] = end;
+        }
+        __syncwarp();
+    }
+}
+
+// side stream: which envs need another segment?  (ext state 0 -> 2)
+__global__ void nav_ahead_scan_kernel(World w, uint32_t *__restrict__ list, uint32_t *__restrict__ count) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= w.E) return;
+    const uint32_t meta = *reinterpret_cast<volatile uint32_t *>(w.nav_meta + e);
+    if ((int)((meta & 0xFFFFu) - (meta >> 16)) < NAV_LOW && (*reinterpret_cast<volatile uint32_t *>(&w.ext_info[e].x) & 3u) == 0u) {
+        w.ext_info[e].x = 2u;
+        list[atomicAdd(count, 1u)] = (uint32_t)e;
+    }
+}
+
+// side stream: plan one segment per listed env from a snapshot of its state into the hand-over slot (ext state 2 -> 1)
+__global__ void __launch_bounds__(32) nav_ahead_plan_kernel(World w, const uint32_t *__restrict__ list, uint32_t *__restrict__ count) {
+    __shared__ PhiloxNavScratch s;
+    const int lane = threadIdx.x;
+    const int n = (int)*count;
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        const int e = (int)list[i];
+        const uint32_t episode = *reinterpret_cast<volatile uint32_t *>(w.episode + e);
+        const uint32_t base = *reinterpret_cast<volatile uint32_t *>(w.nav_meta + e) & 0xFFFFu;
+        __threadfence();
+        const uint32_t start = *reinterpret_cast<volatile uint32_t *>(w.nav_end + e);
+        load_gen_maze(w, e, s.bm, lane);
+        uint32_t goal, end;
+        uint8_t *out = w.ext_plan + (size_t)e * T2D_NAV_PLAN_BYTES;
+        const int len = plan_segment(w, e, episode, (int)base, start, out, 0, s, blockIdx.x, lane, goal, end);
+        if (lane == 0) {
+            w.ext_info[e].y = base | ((uint32_t)len << 16);
+            w.ext_info[e].z = goal & 0xFFFFu;
+            w.ext_info[e].w = end;
+            __threadfence();
+            w.ext_info[e].x = 1u | ((episode & 0xFFFFFFu) << 8);
+        }
+        __syncwarp();
+    }
+    // the last CTA clears the queue for the next scan
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(count + 1, 1u) == gridDim.x - 1) { count[0] = 0; count[1] = 0; }
+    }
+}
+
+// main stream, between steps: append finished segments that still fit (same episode, same length as when they were planned)
+__global__ void nav_merge_kernel(World w) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= w.E) return;
+    if (!(*reinterpret_cast<volatile uint32_t *>(&w.ext_info[e].x) & 1u)) return;
+    __threadfence();
+    uint4 info;
+    info.x = *reinterpret_cast<volatile uint32_t *>(&w.ext_info[e].x);
+    info.y = *reinterpret_cast<volatile uint32_t *>(&w.ext_info[e].y);
+    info.z = *reinterpret_cast<volatile uint32_t *>(&w.ext_info[e].z);
+    info.w = *reinterpret_cast<volatile uint32_t *>(&w.ext_info[e].w);
+    const uint32_t meta = w.nav_meta[e], base = info.y & 0xFFFFu, len = info.y >> 16;
+    if ((info.x >> 8) == (w.episode[e] & 0xFFFFFFu) && base == (meta & 0xFFFFu)) {
+        uint8_t *plan = w.nav_plan + (size_t)e * T2D_NAV_PLAN_BYTES;
+        const uint8_t *src = w.ext_plan + (size_t)e * T2D_NAV_PLAN_BYTES;
+        for (uint32_t i = 0; i < len; i++) plan_put(plan, (int)(base + i), plan_get(src, (int)i));
+        w.nav_goal[e] = info.z;
+        w.nav_end[e] = info.w;
+        __threadfence();  // a planner that sees the new length also sees the new end cell
+        atomicAdd(&w.nav_meta[e], len);
+    }
+    __threadfence();
+    w.ext_info[e].x = 0u;
+}
+
+// main stream: an auto-reset as a copy of the standby world sw (prepared on the side stream) into the live world w.  One warp per
+// finished env (queued by the step kernel); writes the reset observation; queues the env for a new standby world.
+template <typename ObsT>
+__global__ void __launch_bounds__(128) swap_standby_kernel(World w, World sw, ObsT *obs, uint32_t *__restrict__ regen_list, uint32_t *__restrict__ regen_count) {
+    __shared__ uint32_t bms[4][T2D_MAP_WORDS];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int n = (int)w.work_count[0];
+    for (int i = blockIdx.x * 4 + wib; i < n; i += gridDim.x * 4) {
+        const int e = (int)w.work_list[i];
+        uint32_t *bm = bms[wib];
+        const uint32_t *src = sw.maps + (size_t)e * T2D_MAP_WORDS;
+        uint32_t *dst = w.maps + (size_t)e * T2D_MAP_WORDS;
+        for (int k = lane; k < T2D_MAP_WORDS; k += 32) { const uint32_t v = src[k]; bm[k] = v; dst[k] = v; }
+        const uint32_t p = sw.pos[e];
+        if (w.nav_plan) {
+            const uint32_t *ps = reinterpret_cast<const uint32_t *>(sw.nav_plan + (size_t)e * T2D_NAV_PLAN_BYTES);
+            uint32_t *pd = reinterpret_cast<uint32_t *>(w.nav_plan + (size_t)e * T2D_NAV_PLAN_BYTES);
+            for (int k = lane; k < T2D_NAV_PLAN_BYTES / 4; k += 32) pd[k] = ps[k];
+        }
+        __syncwarp();
+        if (lane == 0) {
+            w.pos[e] = p;
+            w.goals[e] = sw.goals[e];
+            w.ctr[e] = 0;
+            if (w.ram) w.ram[e] = sw.ram[e];
+            if (w.nav_plan) {
+                w.nav_goal[e] = sw.nav_goal[e];
+                w.nav_end[e] = sw.nav_end[e];
+                __threadfence();  // map, plan and end cell before the new length / episode (the side-stream planner reads them in the opposite order)
+                w.nav_meta[e] = sw.nav_meta[e];
+            }
+            const uint32_t ep = w.episode[e] + 1u;
+            w.episode[e] = ep;
+            sw.episode[e] = ep;  // key of the next standby world
+            regen_list[atomicAdd(regen_count, 1u)] = (uint32_t)e;
+        }
+        __syncwarp();
+        if (obs) write_partial_obs(bm, p, obs + (size_t)e * T2D_ENV_CELLS, lane);
+        __syncwarp();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&w.work_count[2], 1u) == gridDim.x - 1) {
+            w.stats[0] += w.work_count[0];
+            regen_count[3] = w.work_count[0];  // (the standby reset kernel consumes and clears regen_count[0]; the fill kernel reads [3])
+            w.work_count[0] = 0;
+            w.work_count[2] = 0;
+            __threadfence();
+        }
+    }
+}
+
+// the synchronous fallback in plan-ahead mode: a starved env (cursor == length) gets its next segment appended on the main stream
+__global__ void nav_starved_scan_kernel(World w) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= w.E) return;
+    const uint32_t meta = w.nav_meta[e];
+    if (((meta >> 16) & 0xFFFFu) == (meta & 0xFFFFu)) w.work_list[w.E + atomicAdd(&w.work_count[1], 1u)] = (uint32_t)e;
+}
+__global__ void __launch_bounds__(32) nav_starved_plan_kernel(World w) {
+    __shared__ PhiloxNavScratch s;
+    const int lane = threadIdx.x;
+    const int n = (int)w.work_count[1];
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        const int e = (int)w.work_list[w.E + i];
+        load_gen_maze(w, e, s.bm, lane);
+        const uint32_t meta = w.nav_meta[e], p = w.pos[e];
+        uint32_t goal, end;
+        const uint32_t start = ((p >> 16) & 255u) | ((p >> 24) << 8);
+        const int len = plan_segment(w, e, w.episode[e], (int)(meta & 0xFFFFu), start, w.nav_plan + (size_t)e * T2D_NAV_PLAN_BYTES, (int)(meta & 0xFFFFu), s,
+                                     blockIdx.x, lane, goal, end);
+        if (lane == 0) {
+            w.nav_meta[e] = meta + (uint32_t)len;
+            w.nav_goal[e] = goal & 0xFFFFu;
+            w.nav_end[e] = end;
         }
         __syncwarp();
     }
@@ -731,7 +968,7 @@ __global__ void seed_numpy_kernel(World w, int first, int count, unsigned long l
 
 } // namespace
 
-#define T2D_NAV_GRID (148 * 4)
+#define T2D_NAV_GRID (148 * 10) /* one-warp planners in flight: ~20 KB of shared memory each */
 
 template <typename ObsT, int MAP>
 static cudaError_t launch_reset_map(const World &w, const uint8_t *mask, int from_list, ObsT *obs, int init_only, cudaStream_t s) {
@@ -781,6 +1018,28 @@ cudaError_t t2d_launch_nav_replan(const World &w, cudaStream_t s) {
 }
 cudaError_t t2d_launch_astar_direct(const World &w, int first, int count, const int32_t *sg_dev, int32_t *len_dev, cudaStream_t s) {
     astar_direct_kernel<<<min(count, T2D_NAV_GRID), 32, 0, s>>>(w, first, count, sg_dev, len_dev);
+    return cudaGetLastError();
+}
+// ---- plan-ahead launchers (see the block comment above nav_fill_kernel) ------------------------------------------------------------
+cudaError_t t2d_launch_nav_fill(const World &w, const uint8_t *mask, const uint32_t *list, const uint32_t *count, cudaStream_t s) {
+    nav_fill_kernel<<<min(w.E, T2D_NAV_GRID), 32, 0, s>>>(w, mask, list, count);
+    return cudaGetLastError();
+}
+cudaError_t t2d_launch_nav_ahead(const World &w, uint32_t *list, uint32_t *count, cudaStream_t s) {
+    nav_ahead_scan_kernel<<<(w.E + 255) / 256, 256, 0, s>>>(w, list, count);
+    nav_ahead_plan_kernel<<<T2D_NAV_GRID, 32, 0, s>>>(w, list, count);
+    return cudaGetLastError();
+}
+cudaError_t t2d_launch_nav_merge(const World &w, cudaStream_t s) {
+    nav_merge_kernel<<<(w.E + 255) / 256, 256, 0, s>>>(w);
+    nav_starved_scan_kernel<<<(w.E + 255) / 256, 256, 0, s>>>(w);
+    nav_starved_plan_kernel<<<T2D_NAV_GRID, 32, 0, s>>>(w);
+    finish_replan_kernel<<<1, 32, 0, s>>>(w);
+    return cudaGetLastError();
+}
+cudaError_t t2d_launch_swap_standby(const World &w, const World &sw, void *obs, int obs_u8, uint32_t *regen_list, uint32_t *regen_count, cudaStream_t s) {
+    if (obs_u8) swap_standby_kernel<uint8_t><<<148 * 2, 128, 0, s>>>(w, sw, (uint8_t *)obs, regen_list, regen_count);
+    else swap_standby_kernel<float><<<148 * 2, 128, 0, s>>>(w, sw, (float *)obs, regen_list, regen_count);
     return cudaGetLastError();
 }
 int t2d_nav_slots() { return T2D_NAV_GRID; }

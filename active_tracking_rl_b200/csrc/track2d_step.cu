@@ -161,9 +161,10 @@ __global__ void __launch_bounds__(THREADS) step_kernel(World w, const int32_t *_
                 w.ram[e] = word;
             } else if (TARGET == 2) { // Navigator.step (navigator.py:11-36); exhausted plans were re-planned by nav_replan_kernel
                 uint32_t meta = w.nav_meta[e];
-                uint32_t idx = meta >> 16;
+                uint32_t idx = (meta >> 16) & (TRACK2D_NAV_MAXPLAN - 1);  // (the plan is a ring when it is fed ahead of time)
                 act.y = (w.nav_plan[(size_t)e * T2D_NAV_PLAN_BYTES + (idx >> 2)] >> (2 * (idx & 3))) & 3;
-                w.nav_meta[e] = meta + 0x10000u;
+                if (w.async_nav) atomicAdd(&w.nav_meta[e], 0x10000u);  // the planner's merge adds to the length field concurrently
+                else w.nav_meta[e] = meta + 0x10000u;
             }
 
             // _next_state (track_1v1.py:271-285): stay put when the destination is a wall; agents may overlap

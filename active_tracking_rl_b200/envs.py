@@ -32,7 +32,7 @@ class Track2DVecEnv(object):
 
     def __init__(self, env_id=None, num_envs=1, device="cuda:0", seed=1, rng="philox", auto_reset=True,
                  keep_f64=False, obs_dtype=torch.float32, map_type=None, obs_type=None, target_mode=None, level=0,
-                 max_episode_steps=500):
+                 max_episode_steps=500, plan_ahead=False):
         if env_id is not None:
             map_type, obs_type, target_mode, level = _lib.parse_env_id(env_id)
         if obs_type not in _lib.OBS:
@@ -50,7 +50,9 @@ class Track2DVecEnv(object):
         self.auto_reset = bool(auto_reset)
         assert obs_dtype in (torch.float32, torch.uint8)
         self.obs_dtype = obs_dtype
-        flags = (_lib.FLAG_AUTO_RESET if auto_reset else 0) | (_lib.FLAG_KEEP_F64 if keep_f64 else 0)
+        # plan_ahead: prepare next-episode worlds / Nav plans ahead of time on a side stream instead of inside step() (same results)
+        flags = ((_lib.FLAG_AUTO_RESET if auto_reset else 0) | (_lib.FLAG_KEEP_F64 if keep_f64 else 0)
+                 | (_lib.FLAG_PLAN_AHEAD if plan_ahead else 0))
         cfg = _lib.Config(_lib.ABI_VERSION, self.num_envs, _lib.MAP[map_type], _lib.OBS[obs_type], _lib.TARGET[target_mode],
                           int(level), _lib.RNG[rng], self.device.index, int(max_episode_steps), flags, int(seed) & (2 ** 64 - 1))
         h = C.c_void_p(0)
@@ -133,6 +135,11 @@ class Track2DVecEnv(object):
         fn = self.lib.track2d_step_host if obs_host.dtype == torch.float32 else self.lib.track2d_step_host_u8
         _lib.check(fn(self.h, _ptr(actions_host), _ptr(obs_host), _ptr(reward_host), _ptr(done_host)), self.lib)
         return obs_host, reward_host, done_host
+
+    def join(self):
+        """make the current stream wait for the handle's side-stream work (standby worlds, plans made ahead): call before a CUDA-graph
+        capture containing step() ends; a no-op for handles without side work"""
+        _lib.check(self.lib.track2d_join(self.h, self._stream()), self.lib)
 
     def step_host_begin(self, actions_host, obs_host, reward_host, done_host, n_chunks=8):
         """pipelined step_host: enqueue H2D actions, kernels and the D2H of obs in n_chunks pieces; host_chunk_wait(c) blocks until

@@ -255,6 +255,7 @@ class Agent(object):
         `device_share` are accepted for call compatibility: the model IS the shared model here."""
         T, E = self.t, self.num_envs
         assert T > 0
+        self.env.join()  # side-stream work of the env (standby worlds, plans made ahead) rejoins the learner's stream once per rollout
         if self.engine is not None:
             return self._optimize_fused(T, optimizer, training_mode, world_size, allreduce, boot_forced_actions, apply)
         with torch.no_grad():  # player_util.py:110-116, value only matters where the episode is still running

@@ -47,7 +47,12 @@ enum { T2D_RNG_PHILOX = 0, T2D_RNG_NUMPY = 1 };
 
 enum {
     T2D_FLAG_AUTO_RESET = 1, /* step(): envs that finish are reset in the same call and their obs replaced by the reset obs */
-    T2D_FLAG_KEEP_F64 = 2    /* keep the float64 rewards of the last step for track2d_get_rewards_f64 */
+    T2D_FLAG_KEEP_F64 = 2,   /* keep the float64 rewards of the last step for track2d_get_rewards_f64 */
+    T2D_FLAG_PLAN_AHEAD = 4  /* T2D_RNG_PHILOX + T2D_FLAG_AUTO_RESET handles only: prepare next-episode worlds (Maze maps, Nav targets) and Nav
+                              * plans AHEAD of time on a side stream instead of inside step().  The results are identical either way
+                              * (counter-based RNG; tests/test_gpu_fullsize.py); whether it is faster depends on what else runs on the
+                              * device: kernels that fill the register file / shared memory of every SM (the learner's GEMMs) leave no
+                              * room for the planners to run beside them.  track2d_set_nav is refused. */
 };
 
 enum {
@@ -132,6 +137,11 @@ int track2d_step_host(track2d_env *env, const int32_t *actions_host, float *obs_
 /* the same with uint8 observations (values 0,1,2,4): a quarter of the PCIe traffic; the consumer converts after upload */
 int track2d_reset_host_u8(track2d_env *env, const uint8_t *mask_host, uint8_t *obs_host);
 int track2d_step_host_u8(track2d_env *env, const int32_t *actions_host, uint8_t *obs_host, float *reward_host, uint8_t *done_host);
+
+/* Makes `stream` wait for the work this handle still has in flight on its side stream (standby worlds, plans made ahead of time).
+ * Needed before a CUDA-graph capture that contains track2d_step calls ends, and before reading state another way than through this
+ * API; a no-op for handles without side work.  Never blocks the host. */
+int track2d_join(track2d_env *env, void *stream);
 
 /* The pipelined form of track2d_step_host[_u8]: same transition, but the observation D2H is issued as n_chunks (1..16) pieces of
  * consecutive envs and the call returns after ENQUEUEING.  track2d_host_chunk_wait(env, c) blocks until chunk c -- envs

@@ -160,3 +160,40 @@ def test_pipelined_host_step_equals_host_step(t2d, obs_dtype, n_chunks):
     assert a.status() == 0 and b.status() == 0
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("env_id,E,T", [("Track2D-BlockPartialNav-v0", 384, 260), ("Track2D-MazePartialNav-v0", 200, 200),
+                                        ("Track2D-MazePartialAdv-v0", 512, 120), ("Track2D-MazePartialRam-v0", 256, 120)])
+def test_planning_ahead_equals_synchronous_planning(t2d, env_id, E, T):
+    """T2D_FLAG_PLAN_AHEAD: Philox + auto-reset handles prepare next-episode worlds and Nav plans AHEAD of time on a side stream (standby
+    worlds, plan ring) instead of inside step().  Counter-based RNG: WHEN something is computed must not change WHAT comes out --
+    positions, executed target actions, rewards, dones and observations are identical step by step, across many resets and replans."""
+    a = t2d.Track2DVecEnv(env_id, num_envs=E, seed=77, rng="philox", auto_reset=True, obs_dtype=torch.uint8, plan_ahead=True)
+    b = t2d.Track2DVecEnv(env_id, num_envs=E, seed=77, rng="philox", auto_reset=True, obs_dtype=torch.uint8)
+    oa, ob = a.reset().clone(), b.reset().clone()
+    assert torch.equal(oa, ob) and (a.get_maps() == b.get_maps()).all() and (a.get_agents()[0] == b.get_agents()[0]).all()
+    rs = np.random.RandomState(4)
+    n_done = 0
+    for t in range(T):
+        pos, _ = b.get_agents()
+        d = pos[:, 1] - pos[:, 0]  # most trackers chase their target (long episodes: plans run out), the rest wander off (resets)
+        chase = np.where(np.abs(d[:, 0]) >= np.abs(d[:, 1]), np.where(d[:, 0] < 0, 0, 1), np.where(d[:, 1] < 0, 2, 3))
+        a0 = np.where(np.arange(E) % 4 == 0, rs.randint(0, 4, E), chase)
+        acts = torch.from_numpy(np.stack([a0, rs.randint(0, 4, E)], 1).astype(np.int32)).cuda()
+        xa, ra, da = a.step(acts)
+        xb, rb, db = b.step(acts)
+        a.join()
+        assert torch.equal(da, db), t
+        assert torch.equal(ra, rb), t
+        assert torch.equal(xa, xb), t
+        pa, ca = a.get_agents()
+        pb, cb = b.get_agents()
+        assert (pa == pb).all() and (ca == cb).all(), t
+        if a.target_mode in ("Nav", "Ram"):
+            assert (a.get_target_actions() == b.get_target_actions()).all(), t
+        n_done += int(da.sum())
+    assert n_done > E // 4, n_done
+    assert a.status() == 0 and b.status() == 0
+    assert a.counters() == b.counters()
+    a.close()
+    b.close()

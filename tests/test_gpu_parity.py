@@ -455,7 +455,8 @@ def test_philox_navigator_plans_are_valid_shortest_paths(t2d, env_id):
         plan, ln, idx, goal = env.get_nav()
         env.step(acts)
         tgt = env.get_target_actions()
-        cont = idx < ln  # no replan needed before this step: the executed action is the planned one
+        cont = idx < ln  # no (re)plan needed before this step: the executed action is the planned one (ln == 0: first plan of an episode an
+        #                  auto-reset started -- it is made by the replan wave of the next step)
         assert (tgt[cont] == plan[np.arange(E), np.minimum(idx, 1023)][cont]).all()
         replans += int((~cont).sum())
         if t % 40 == 39:
