@@ -22,6 +22,10 @@ class Agent(object):
         self.args = args
         self.device = torch.device(device)
         self.num_agents = len(env.observation_space)
+        if self.num_agents != 2 or bool(getattr(args, 'single', False)):
+            # the rollout buffers, the GAE / loss kernels and optimize() are written for the tracker-target pair of the 2D path
+            raise NotImplementedError("single-agent mode (--single) is not built: the 2D path always has a tracker and a target "
+                                      "(scripted targets Ram / Nav / RPF ignore the second policy's action)")
         self.num_envs = env.num_envs
         self.dim_action = 1
         self.rnn_out = args.rnn_out
