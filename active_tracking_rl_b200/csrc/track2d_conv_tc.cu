@@ -280,6 +280,193 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) conv_tc_fwd_kernel(const XT *_
 }
 
 // =====================================================================================================================
+// forward, version 2: NO im2col gather.  conv1 writes y1 (split hi / lo) straight into six small arrays, one per (row parity, kj):
+//     C[pr][kj][a][oj] = y1pad[2 a + pr][2 oj + kj]            (y1pad = the 7x7 map inside a zero border, 9 x 9)
+// each element holding [4 channel quads][8 images][4 channels] = 512 bytes.  For tap (ki, kj) the 16 output positions then read
+// elements (oi + ki/2) * 4 + oj = position + 4 * (ki / 2) of array C[ki & 1][kj]: consecutive positions, constant stride -- so the A
+// operand of that tap IS a K-major, no-swizzle UMMA operand in place (8-row core matrix = 8 images x 16 bytes, SBO = 512 to the next
+// position, LBO = 128 to the next channel quad), addressed by moving the descriptor's start address.  Every y1 value is stored 1.4
+// times on average (x 2 for hi / lo) instead of being copied 2.9 times (x 2) out of a staging tile: a third of the shared-memory
+// traffic of version 1, and the eight gather warps are gone.
+//   warps 0..3   epilogue (as version 1)      warp 4   MMA      warps 5..18   conv1: warp = (output row, column half), lane = (image, channel quad)
+constexpr int V2_ARR0 = 20 * 512, V2_ARR1 = 16 * 512;                  // bytes of an array with row parity 0 (5 x 4 elements) / 1 (4 x 4)
+constexpr int V2_PLANE = 3 * (V2_ARR0 + V2_ARR1);                       // 55,296: one of hi / lo
+constexpr int V2_OFF_B = 0, V2_OFF_A = B_BYTES, V2_OFF_XS = V2_OFF_A + 2 * V2_PLANE, V2_OFF_OUT = V2_OFF_XS + 2 * XS_BYTES,
+              V2_OFF_BAR = V2_OFF_OUT + OUT_BYTES, V2_SMEM = V2_OFF_BAR + 256 + 1024;
+constexpr int V2_C1_WARPS = 14, V2_THREADS = (5 + V2_C1_WARPS) * 32;    // 608: warp = (output row, column half)
+static_assert(V2_OFF_A % 1024 == 0 && V2_OFF_XS % 16 == 0 && V2_OFF_OUT % 16 == 0 && V2_OFF_BAR % 8 == 0 && V2_SMEM <= 227 * 1024, "layout");
+__host__ __device__ constexpr int v2_arr_base(int pr, int kj) { return pr == 0 ? kj * V2_ARR0 : 3 * V2_ARR0 + kj * V2_ARR1; }
+
+template <typename XT>
+__global__ void __launch_bounds__(V2_THREADS, 1) conv_tc_fwd2_kernel(const XT *__restrict__ x, long long xs, long long N, const float *__restrict__ w1,
+                                                                    const float *__restrict__ b1, const float *__restrict__ w2,
+                                                                    const float *__restrict__ b2, float *__restrict__ y2) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw0 = smem_u32(smem_raw);
+    const uint32_t smem0 = (raw0 + 1023u) & ~1023u;
+    uint8_t *sm = smem_raw + (smem0 - raw0);
+    const uint32_t bars = smem0 + V2_OFF_BAR;
+    const uint32_t bar_af = bars, bar_ae = bars + 8, bar_accf = bars + 16, bar_acce = bars + 32, tmem_slot = bars + 48;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long n_tiles = (N + IMGS - 1) / IMGS;
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar_af, V2_C1_WARPS * 32);
+        mbar_init(bar_ae, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(bar_accf + 8 * b, 1);
+            mbar_init(bar_acce + 8 * b, EPI_WARPS * 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == MMA_WARP) tmem_alloc(tmem_slot, TMEM_COLS);
+    for (int i = threadIdx.x; i < 32 * 144; i += V2_THREADS) {  // the weights: 9 K-major SWIZZLE_64B blocks, hi | lo (as version 1)
+        const int oc = i / 144, rem = i - oc * 144, ic = rem / 9, tap = rem - ic * 9;
+        float hi, lo;
+        split1(w2[i], hi, lo);
+        const uint32_t off = (uint32_t)(tap * B_BLOCK) + kmajor_off(oc, ic >> 2) + (uint32_t)(ic & 3) * 4u;
+        *reinterpret_cast<float *>(sm + V2_OFF_B + off) = hi;
+        *reinterpret_cast<float *>(sm + V2_OFF_B + 9 * B_BLOCK + off) = lo;
+    }
+    for (int i = threadIdx.x; i < (2 * V2_PLANE + 2 * XS_BYTES) / 4; i += V2_THREADS) reinterpret_cast<uint32_t *>(sm + V2_OFF_A)[i] = 0u;  // zero borders
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(sm + V2_OFF_BAR + (tmem_slot - bars));
+
+    if (warp >= 5) {
+        // ===== conv1 + ReLU, split, direct operand stores =====
+        const int ct = threadIdx.x - 5 * 32;
+        const int row = ct >> 6, half = (ct >> 5) & 1, img = lane & 7, q = lane >> 3;  // a quarter-warp = 8 images of one channel quad
+        float4 w[9], bias;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) w[k] = make_float4(__ldg(w1 + (4 * q) * 9 + k), __ldg(w1 + (4 * q + 1) * 9 + k), __ldg(w1 + (4 * q + 2) * 9 + k), __ldg(w1 + (4 * q + 3) * 9 + k));
+        bias = make_float4(__ldg(b1 + 4 * q), __ldg(b1 + 4 * q + 1), __ldg(b1 + 4 * q + 2), __ldg(b1 + 4 * q + 3));
+        constexpr int PRE = (IMGS * 169 + V2_C1_WARPS * 32 - 1) / (V2_C1_WARPS * 32);  // 4
+        uint32_t pre[PRE];
+#pragma unroll
+        for (int j = 0; j < PRE; ++j) pre[j] = load_px(x, xs, N, (long long)blockIdx.x * IMGS, ct + V2_C1_WARPS * 32 * j);
+        const int pr = (row + 1) & 1, a = (row + 1) >> 1;  // padded row r' = row + 1 = 2 a + pr
+        // byte offsets of this thread's 16-byte slot inside element (a, oj = 0) of the three arrays of its row parity
+        const uint32_t slot0 = smem0 + V2_OFF_A + (uint32_t)(a * 4 * 512 + q * 128 + img * 16);
+        const uint32_t arr0 = slot0 + (uint32_t)(pr ? v2_arr_base(1, 0) : v2_arr_base(0, 0)), arr1 = slot0 + (uint32_t)(pr ? v2_arr_base(1, 1) : v2_arr_base(0, 1)),
+                       arr2 = slot0 + (uint32_t)(pr ? v2_arr_base(1, 2) : v2_arr_base(0, 2));
+        int it = 0;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            uint8_t *xs8 = sm + V2_OFF_XS + (it & 1) * XS_BYTES;
+#pragma unroll
+            for (int j = 0; j < PRE; ++j) store_px(xs8, ct + V2_C1_WARPS * 32 * j, pre[j]);
+            const long long next = tile + gridDim.x;
+            if (next < n_tiles) {
+#pragma unroll
+                for (int j = 0; j < PRE; ++j) pre[j] = load_px(x, xs, N, next * IMGS, ct + V2_C1_WARPS * 32 * j);
+            }
+            bar_sync(1, V2_C1_WARPS * 32);
+            uint4 win[3];
+#pragma unroll
+            for (int ki = 0; ki < 3; ++ki) win[ki] = *reinterpret_cast<const uint4 *>(xs8 + img * XS_IMG + (2 * row + ki) * 16);
+            // padded column c' = J + 1: odd -> array kj = 1, oj = J / 2; even -> kj = 0 (oj = c' / 2) and kj = 2 (oj = c' / 2 - 1)
+#define T2D_POS(J)                                                                         \
+    {                                                                                      \
+        const float4 t = conv1_at<J>(win, w, bias);                                        \
+        split4(make_float4(fmaxf(t.x, 0.f), fmaxf(t.y, 0.f), fmaxf(t.z, 0.f), fmaxf(t.w, 0.f)), hi[J & 3], lo[J & 3]); \
+    }
+// (handing the six arrays over one by one, each with its own full / empty barrier, was measured and is no faster: the conv1 warps' own
+// per-tile latency chain bounds the kernel, not the wait for the single operand buffer)
+#define T2D_PUT(J)                                                                         \
+    if ((J & 1) == 0) {                                                                    \
+        sts128(arr1 + (J / 2) * 512, hi[J & 3]); sts128(arr1 + (J / 2) * 512 + V2_PLANE, lo[J & 3]); \
+    } else {                                                                               \
+        sts128(arr0 + ((J + 1) / 2) * 512, hi[J & 3]); sts128(arr0 + ((J + 1) / 2) * 512 + V2_PLANE, lo[J & 3]); \
+        sts128(arr2 + ((J + 1) / 2 - 1) * 512, hi[J & 3]); sts128(arr2 + ((J + 1) / 2 - 1) * 512 + V2_PLANE, lo[J & 3]); \
+    }
+            float4 hi[4], lo[4];
+            if (half == 0) {
+                T2D_POS(0) T2D_POS(1) T2D_POS(2) T2D_POS(3)
+                mbar_wait(bar_ae, ((uint32_t)it & 1u) ^ 1u);
+                T2D_PUT(0) T2D_PUT(1) T2D_PUT(2) T2D_PUT(3)
+            } else {
+                T2D_POS(4) T2D_POS(5) T2D_POS(6)
+                mbar_wait(bar_ae, ((uint32_t)it & 1u) ^ 1u);
+                T2D_PUT(4) T2D_PUT(5) T2D_PUT(6)
+            }
+            fence_proxy_async();
+            mbar_arrive(bar_af);
+#undef T2D_POS
+#undef T2D_PUT
+        }
+    } else if (warp == MMA_WARP) {
+        constexpr uint32_t idesc = idesc_tf32(128, 32, 0, 0);
+        const uint64_t abase = umma_desc(0u, 128u, 512u, 0u);  // K-major, no swizzle: LBO = next 4 channels, SBO = next output position
+        const uint64_t bbase = kmajor_desc(0u);
+        int it = 0;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int abuf = it & 1;
+            mbar_wait(bar_acce + 8 * abuf, ((uint32_t)(it >> 1) & 1u) ^ 1u);
+            mbar_wait(bar_af, (uint32_t)it & 1u);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t d = tmem_base + (uint32_t)(abuf * 32);
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) {
+                    const int ki = tap / 3, kj = tap - 3 * ki;
+                    const uint32_t a16 = (smem0 + V2_OFF_A + v2_arr_base(ki & 1, kj) + (ki >> 1) * 4 * 512) >> 4;
+                    const uint32_t b16 = (smem0 + V2_OFF_B + tap * B_BLOCK) >> 4;
+#pragma unroll
+                    for (int k8 = 0; k8 < 2; ++k8) {
+                        const uint64_t a_hi = abase + (a16 + 16 * k8), a_lo = a_hi + (V2_PLANE >> 4);   // two channel quads = 256 bytes per MMA
+                        const uint64_t b_hi = bbase + (b16 + 2 * k8), b_lo = b_hi + ((9 * B_BLOCK) >> 4);
+                        tc_mma_tf32(d, a_lo, b_hi, idesc, (tap | k8) ? 1u : 0u);
+                        tc_mma_tf32(d, a_hi, b_lo, idesc, 1u);
+                        tc_mma_tf32(d, a_hi, b_hi, idesc, 1u);
+                    }
+                }
+                tc_commit(bar_ae);                   // the operand arrays may be refilled
+                tc_commit(bar_accf + 8 * abuf);      // accumulator complete
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===== epilogue (identical to version 1) =====
+        const int et = threadIdx.x;
+        const int img = lane & 7, opos = warp * 4 + (lane >> 3);
+        float bias[32];
+#pragma unroll
+        for (int oc = 0; oc < 32; ++oc) bias[oc] = __ldg(b2 + oc);
+        float *outs = reinterpret_cast<float *>(sm + V2_OFF_OUT);
+        int it = 0;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int abuf = it & 1;
+            mbar_wait_backoff(bar_accf + 8 * abuf, (uint32_t)(it >> 1) & 1u);
+            tc_fence_after();
+            uint32_t r[32];
+            tc_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(abuf * 32), r);
+            tc_wait_ld();
+            tc_fence_before();
+            mbar_arrive(bar_acce + 8 * abuf);
+#pragma unroll
+            for (int oc = 0; oc < 32; ++oc) outs[img * OUT_IMG + oc * 16 + opos] = fmaxf(__uint_as_float(r[oc]) + bias[oc], 0.f);
+            bar_sync(2, EPI_WARPS * 32);
+            const long long n0 = tile * IMGS;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int i4 = et + 128 * j, im = i4 >> 7, off = (i4 & 127) * 4;
+                const float4 v = *reinterpret_cast<const float4 *>(outs + im * OUT_IMG + off);
+                if (n0 + im < N) *reinterpret_cast<float4 *>(y2 + (n0 + im) * 512 + off) = v;
+            }
+            bar_sync(2, EPI_WARPS * 32);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == MMA_WARP) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// =====================================================================================================================
 // backward: given gy2 = dL/dy2, the gradients of all four parameter tensors.  Same tile (8 images, row m = 8 * opos + image) and the same
 // shared-memory gather as the forward; two contractions per tile on the tensor cores:
 //   dCOL [128 x 144] = dz2 [128 x 32] W2 [32 x 144]          A, B K-major (reduction = output channel); then col2im -> dy1 (shared memory)
@@ -726,7 +913,26 @@ int sm_count() {
 }
 
 template <typename XT>
+cudaError_t fwd2_launch(const XT *x, int64_t xs, int64_t n, const float *w1, const float *b1, const float *w2, const float *b2, float *y2, cudaStream_t st) {
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_set[dev & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_fwd2_kernel<XT>, cudaFuncAttributeMaxDynamicSharedMemorySize, V2_SMEM);
+        if (e != cudaSuccess) return e;
+        attr_set[dev & 63] = true;
+    }
+    const int64_t tiles = (n + IMGS - 1) / IMGS;
+    const int sms = sm_count();
+    conv_tc_fwd2_kernel<XT><<<(int)(tiles < sms ? tiles : sms), V2_THREADS, V2_SMEM, st>>>(x, xs, n, w1, b1, w2, b2, y2);
+    return cudaGetLastError();
+}
+
+template <typename XT>
 cudaError_t fwd_launch(const XT *x, int64_t xs, int64_t n, const float *w1, const float *b1, const float *w2, const float *b2, float *y2, cudaStream_t st) {
+    static int use_v1 = -1;  // T2D_CONV_FWD=v1: the gather version (A/B measurements)
+    if (use_v1 < 0) { const char *e = getenv("T2D_CONV_FWD"); use_v1 = (e && strcmp(e, "v1") == 0) ? 1 : 0; }
+    if (!use_v1) return fwd2_launch(x, xs, n, w1, b1, w2, b2, y2, st);
     static bool attr_set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
