@@ -54,6 +54,7 @@ SYMBOLS = {
     "track2d_join": (C.c_int, [_vp, _vp]),
     "track2d_step_host_begin": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp, _i32]),
     "track2d_host_chunk_wait": (C.c_int, [_vp, _i32]),
+    "track2d_host_chunk_wait_stream": (C.c_int, [_vp, _i32, _vp]),
     "track2d_get_maps": (C.c_int, [_vp, _i32, _i32, _vp]),
     "track2d_set_maps": (C.c_int, [_vp, _i32, _i32, _vp]),
     "track2d_get_agents": (C.c_int, [_vp, _i32, _i32, _vp, _vp]),
@@ -76,7 +77,7 @@ SYMBOLS = {
     "track2d_maze_conv_forward_ex": (C.c_int, [_vp, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "track2d_maze_conv_backward_ex": (C.c_int, [_vp, _i32, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "track2d_lstm_heads_forward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                                             C.c_uint64, _u32, _i32, _i64, _vp]),
+                                             C.c_uint64, _u32, _i32, _i64, _i64, _vp]),
     "track2d_policy_post_step": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp]),
     "track2d_embed_add": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _i32, _i64, _vp]),
     "track2d_a3c_loss_grad": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _dbl, _dbl, _dbl, _dbl, _dbl, _i32, _i32, _i32, _vp]),

@@ -66,6 +66,7 @@ struct FwdArgs {
     uint32_t stream;         // Philox stream: agent | bootstrap << 1
     int greedy;
     long long E;
+    long long first_row;     // index of row 0 in the whole batch: the Philox counter of row r is first_row + r (a batch processed in slices samples the same actions)
 };
 
 // one warp per row; lane = 4 consecutive hidden units
@@ -138,7 +139,8 @@ __global__ void __launch_bounds__(WARPS * 32) lstm_heads_fwd_kernel(const FwdArg
                 if (p2 > best) { best = p2; act = 2; }
                 if (p3 > best) { best = p3; act = 3; }
             } else {
-                const uint32_t r = philox_first(a.seed, (uint32_t)row, a.stream | ((uint32_t)(row >> 32) << 8), (uint32_t)step, (uint32_t)(step >> 32));
+                const long long grow = a.first_row + row;
+                const uint32_t r = philox_first(a.seed, (uint32_t)grow, a.stream | ((uint32_t)(grow >> 32) << 8), (uint32_t)step, (uint32_t)(step >> 32));
                 const float u = (float)(r >> 8) * (1.0f / 16777216.0f);  // [0, 1)
                 act = u < p0 ? 0 : (u < p0 + p1 ? 1 : (u < p0 + p1 + p2 ? 2 : 3));
             }
@@ -400,8 +402,8 @@ extern "C" int track2d_lstm_heads_forward(const float *gates_dev, const float *b
                                           float *c_next_dev, float *h_out_dev, float *h_next_dev, int64_t h_next_ld, const float *w_head_dev,
                                           const float *b_head_dev, float *out8_dev, int32_t *action_dev, const int32_t *forced_dev, float *value_dev,
                                           float *logp_dev, float *entropy_dev, float *logp_all_dev, const uint64_t *rng_step_dev, uint64_t seed,
-                                          uint32_t rng_stream, int32_t greedy, int64_t E, void *stream) {
-    if (!gates_dev || !b_ih_dev || !b_hh_dev || !c_prev_dev || !c_next_dev || !w_head_dev || !b_head_dev || !action_dev || E < 1 ||
+                                          uint32_t rng_stream, int32_t greedy, int64_t E, int64_t first_row, void *stream) {
+    if (!gates_dev || !b_ih_dev || !b_hh_dev || !c_prev_dev || !c_next_dev || !w_head_dev || !b_head_dev || !action_dev || E < 1 || first_row < 0 ||
         (!forced_dev && !greedy && !rng_step_dev)) {
         t2d_set_error("track2d_lstm_heads_forward: bad argument");
         return T2D_E_INVALID;
@@ -415,7 +417,7 @@ extern "C" int track2d_lstm_heads_forward(const float *gates_dev, const float *b
     a.gates = gates_dev; a.b_ih = b_ih_dev; a.b_hh = b_hh_dev; a.c_prev = c_prev_dev; a.act = act_dev; a.c_next = c_next_dev; a.h_out = h_out_dev;
     a.h_next = h_next_dev; a.h_next_ld = h_next_ld; a.w_head = w_head_dev; a.b_head = b_head_dev; a.out8 = out8_dev; a.action = action_dev;
     a.forced = forced_dev; a.value = value_dev; a.logp = logp_dev; a.entropy = entropy_dev; a.logp_all = logp_all_dev;
-    a.rng_step = reinterpret_cast<const unsigned long long *>(rng_step_dev); a.seed = seed; a.stream = rng_stream; a.greedy = greedy; a.E = E;
+    a.rng_step = reinterpret_cast<const unsigned long long *>(rng_step_dev); a.seed = seed; a.stream = rng_stream; a.greedy = greedy; a.E = E; a.first_row = first_row;
     lstm_heads_fwd_kernel<<<row_grid(E, WARPS, 8), WARPS * 32, 0, (cudaStream_t)stream>>>(a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail("track2d_lstm_heads_forward", e);

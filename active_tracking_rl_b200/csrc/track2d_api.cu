@@ -539,6 +539,15 @@ int track2d_host_chunk_wait(track2d_env *env, int32_t chunk) {
     T2D_CUDA(cudaEventSynchronize(env->chunk_ev[chunk]));
     return T2D_OK;
 }
+// the same dependency without the host in the middle: work enqueued on `stream` after this call starts once chunk `chunk` is in the
+// host buffers (e.g. its re-upload: the H2D engine then runs one chunk behind the D2H engine with no host wake-up between them)
+int track2d_host_chunk_wait_stream(track2d_env *env, int32_t chunk, void *stream) {
+    T2D_REQUIRE(env, "null handle");
+    T2D_REQUIRE(chunk >= 0 && chunk < env->n_chunk_ev, "host_chunk_wait_stream: no such chunk (call track2d_step_host_begin first)");
+    DeviceGuard guard(env->cfg.device);
+    T2D_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, env->chunk_ev[chunk], 0));
+    return T2D_OK;
+}
 
 // ---- state read-back / injection ---------------------------------------------------------------------
 int track2d_get_maps(track2d_env *env, int32_t first, int32_t count, uint8_t *maze_host) {

@@ -489,8 +489,15 @@ constexpr int BSTAGE_BYTES = 2 * BA_PLANE + 2 * BB_PLANE;  // 24,576
 constexpr int DZA_BYTES = 4 * A_TILE;               // dz2 as the dCOL A operand: [hi | lo] x 2 reduction blocks of 128 x 16
 constexpr int DZT_PITCH = 36;                       // floats per row of the staged dz2 [m][oc]
 constexpr int DZT_BYTES = 128 * DZT_PITCH * 4;
-constexpr int DY_POS = 20, DY_IMG = 49 * DY_POS + 1;  // dy1s [img][pos][ic]: odd image pitch, position pitch 20 -> conflict-free col2im
-constexpr int DY_BYTES = IMGS * DY_IMG * 4;
+// dy1s [img][pos][ic], scalar accesses (a conflict-free scalar store moves 128 bytes per LSU cycle, a 128-bit one half of that -- the
+// float4 layout was measured slower).  Bank of (img, pos, ic) = img offset + 18 pos + ic with the image offsets = {0, 1, 2, 3, 16, 17, 18,
+// 19} mod 32: the col2im lanes (8 images x 4 positions two apart: + {0, 4, 8, 12}) and the dW1 lanes (8 images x 4 channel quads:
+// + {0, 4, 8, 12}) both cover all 32 banks exactly once.
+constexpr int DY_POS = 18, DY_IMG4 = 3600, DY_IMG1 = 897;
+__host__ __device__ constexpr int dy_img(int img) { return (img >> 2) * DY_IMG4 + (img & 3) * DY_IMG1; }
+static_assert(DY_IMG1 % 32 == 1 && DY_IMG4 % 32 == 16 && DY_IMG1 >= 49 * DY_POS && DY_IMG4 >= 4 * DY_IMG1, "dy1s banks");
+constexpr int DY_FLOATS = 2 * DY_IMG4;
+constexpr int DY_BYTES = DY_FLOATS * 4;
 constexpr int BOFF_W2 = 0;
 constexpr int BOFF_RING = BOFF_W2 + BW2_BYTES;                 // 36,864
 constexpr int BOFF_DZA = BOFF_RING + BSTAGES * BSTAGE_BYTES;   // 110,592
@@ -559,7 +566,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) conv_tc_bwd_kernel(const XT *_
         reinterpret_cast<float *>(sm + BOFF_BAR + 256)[i] = v;
     }
     for (int i = threadIdx.x; i < 2 * XS_BYTES / 4; i += BWD_THREADS) reinterpret_cast<uint32_t *>(sm + BOFF_XS)[i] = 0u;
-    for (int i = threadIdx.x; i < IMGS * DY_IMG; i += BWD_THREADS) reinterpret_cast<float *>(sm + BOFF_DY)[i] = 0.f;
+    for (int i = threadIdx.x; i < DY_FLOATS; i += BWD_THREADS) reinterpret_cast<float *>(sm + BOFF_DY)[i] = 0.f;
     for (int i = threadIdx.x; i < BSTAGES * BSTAGE_BYTES / 4; i += BWD_THREADS) reinterpret_cast<float *>(sm + BOFF_RING)[i] = 0.f;  // rows 144..159 stay 0
     fence_proxy_async();
     tc_fence_before();
@@ -732,7 +739,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) conv_tc_bwd_kernel(const XT *_
                 uint4 win[3];
 #pragma unroll
                 for (int ki = 0; ki < 3; ++ki) win[ki] = *reinterpret_cast<const uint4 *>(xs8 + img * XS_IMG + (2 * row + ki) * 16);
-                float *dy = reinterpret_cast<float *>(sm + BOFF_DY) + img * DY_IMG + (row * 7) * DY_POS + 4 * q;
+                float *dy = reinterpret_cast<float *>(sm + BOFF_DY) + dy_img(img) + (row * 7) * DY_POS + 4 * q;
 #define T2D_TAP(J, KI, KJ)                                                                     \
     {                                                                                          \
         const float v = win_px<2 * J + KJ>(win[KI]);                                           \
@@ -834,7 +841,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) conv_tc_bwd_kernel(const XT *_
     } else {
         // ===== epilogue: col2im of dCOL, finally the dW2 read-out =====
         const int img = lane & 7, opos = warp * 4 + (lane >> 3), oi = opos >> 2, oj = opos & 3;
-        float *dy = reinterpret_cast<float *>(sm + BOFF_DY) + img * DY_IMG;
+        float *dy = reinterpret_cast<float *>(sm + BOFF_DY) + dy_img(img);
         int it = 0;
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int abuf = it & 1;

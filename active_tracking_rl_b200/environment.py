@@ -13,4 +13,4 @@ def create_env(env_id, args, num_envs=None, device=None, seed=None, rng="philox"
     E = int(num_envs if num_envs is not None else getattr(args, 'num_envs', 1))
     dev = device if device is not None else getattr(args, 'device', 'cuda:0')
     sd = seed if seed is not None else getattr(args, 'seed', 1)
-    return Track2DVecEnv(env_id, num_envs=E, device=dev, seed=sd, rng=rng, auto_reset=True)
+    return Track2DVecEnv(env_id, num_envs=E, device=dev, seed=sd, rng=rng, auto_reset=True, plan_ahead=bool(getattr(args, 'plan_ahead', False)))

@@ -147,8 +147,13 @@ class Track2DVecEnv(object):
         _lib.check(self.lib.track2d_step_host_begin(self.h, _ptr(actions_host), _ptr(obs_host), int(obs_host.dtype == torch.uint8), _ptr(reward_host),
                                                     _ptr(done_host), int(n_chunks)), self.lib)
 
-    def host_chunk_wait(self, chunk):
-        _lib.check(self.lib.track2d_host_chunk_wait(self.h, int(chunk)), self.lib)
+    def host_chunk_wait(self, chunk, on_stream=False):
+        """block the host until chunk `chunk` is in the host buffers; on_stream: make the current CUDA stream wait for it instead (what
+        is enqueued next -- the re-upload -- starts the moment the chunk has landed, with no host wake-up in between)"""
+        if on_stream:
+            _lib.check(self.lib.track2d_host_chunk_wait_stream(self.h, int(chunk), self._stream()), self.lib)
+        else:
+            _lib.check(self.lib.track2d_host_chunk_wait(self.h, int(chunk)), self.lib)
 
     def chunk_bounds(self, chunk, n_chunks):
         E = self.num_envs

@@ -163,44 +163,54 @@ class FusedA3C(object):
 
     # ---- forward -------------------------------------------------------------------------------------------------------
     @torch.no_grad()
-    def forward(self, t, forced=None, greedy=False, bootstrap=False):
+    def forward(self, t, forced=None, greedy=False, bootstrap=False, envs=None):
         """policy step `t` from self.obs[t] and the recurrent state in slot t: fills actions[t], values[t], logp[t],
         entropy[t] and the state of slot t + 1.  `bootstrap`: the value-only forward of Agent.optimize (player_util.py:110-116;
-        it still samples, as the reference does) -- nothing is kept for the backward."""
+        it still samples, as the reference does) -- nothing is kept for the backward.  `envs` = (first, end): only that slice of the
+        batch (every kernel is row-wise and the sampler's counter is the env index, so slices add up to exactly the whole-batch step;
+        Agent uses it to start on the envs whose observations have already arrived over PCIe)."""
         with _lib.on_device(self.device):
-            return self._forward(t, forced, greedy, bootstrap)
+            return self._forward(t, forced, greedy, bootstrap, envs)
 
-    def _forward(self, t, forced, greedy, bootstrap):
-        lib, E, st = self.lib, self.E, self._stream()
+    def _forward(self, t, forced, greedy, bootstrap, envs=None):
+        lib, st = self.lib, self._stream()
+        e0, e1 = (0, self.E) if envs is None else (int(envs[0]), int(envs[1]))
+        if not 0 <= e0 < e1 <= self.E:
+            raise ValueError("forward: env slice [%d, %d) outside [0, %d)" % (e0, e1, self.E))
+        E = e1 - e0
         if self._dirty:
             self.pack()
         obs = self.obs[t]
+        row = lambda buf, width: C.c_void_p(buf.data_ptr() + 4 * width * e0)  # noqa: E731  row e0 of a float32 / int32 [E][width] array
         for n in self.nets:
             a, m = n.agent, n.m
             enc = m.encoder
             if n.tat:
-                x_ptr, stride, n_img = obs.data_ptr(), 169, 2 * E
+                x_ptr, stride, n_img = obs.data_ptr() + 338 * e0, 169, 2 * E
             else:
-                x_ptr, stride, n_img = obs.data_ptr() + 169 * a, 338, E
+                x_ptr, stride, n_img = obs.data_ptr() + 338 * e0 + 169 * a, 338, E
+            convout, xh_t = n.convout[t, e0:e1], n.xh[t, e0:e1]
+            gates = n.gates[e0:e1]
             _lib.check(lib.track2d_maze_conv_forward_ex(C.c_void_p(x_ptr), 1, stride, n_img, _p(enc.conv1.weight), _p(enc.conv1.bias),
-                                                        _p(enc.conv2.weight), _p(enc.conv2.bias), _p(n.convout[t]), st), lib)
-            feat = n.xh[t, :, :256]
+                                                        _p(enc.conv2.weight), _p(enc.conv2.bias), _p(convout), st), lib)
+            feat = xh_t[:, :256]
             if n.tat:
-                gemm.gemm(n.convout[t], False, n.F, enc.fc.weight, False, n.F, E, 256, n.F, bias=enc.fc.bias, relu=True, out=n.yfc[t])
+                yfc = n.yfc[t, e0:e1]
+                gemm.gemm(convout, False, n.F, enc.fc.weight, False, n.F, E, 256, n.F, bias=enc.fc.bias, relu=True, out=yfc)
                 # model.py:198-199: + fc_action_tracker(one_hot(tracker action)), added after the ReLU
-                _lib.check(lib.track2d_embed_add(_p(n.yfc[t]), 256, _p(feat), 384, _p(m.fc_action_tracker.weight), _p(m.fc_action_tracker.bias),
-                                                 _p(self.actions[t]), 256, E, st), lib)
+                _lib.check(lib.track2d_embed_add(_p(yfc), 256, _p(feat), 384, _p(m.fc_action_tracker.weight), _p(m.fc_action_tracker.bias),
+                                                 row(self.actions[t], 2), 256, E, st), lib)
             else:
-                gemm.gemm(n.convout[t], False, n.F, enc.fc.weight, False, n.F, E, 256, n.F, bias=enc.fc.bias, relu=True, out=feat)
-            gemm.gemm(n.xh[t], False, 384, n.w_cat, False, 384, E, 4 * H, 384, out=n.gates)
+                gemm.gemm(convout, False, n.F, enc.fc.weight, False, n.F, E, 256, n.F, bias=enc.fc.bias, relu=True, out=feat)
+            gemm.gemm(xh_t, False, 384, n.w_cat, False, 384, E, 4 * H, 384, out=gates)
             keep = not bootstrap
-            col = lambda buf: C.c_void_p(buf[t].data_ptr() + 4 * a)  # noqa: E731  column `a` of an [E][2] array
+            col = lambda buf: C.c_void_p(buf[t].data_ptr() + 4 * (2 * e0 + a))  # noqa: E731  column `a` of an [E][2] array, from row e0
             _lib.check(lib.track2d_lstm_heads_forward(
-                _p(n.gates), _p(m.lstm.bias_ih), _p(m.lstm.bias_hh), _p(n.c[t]), _p(n.act[t]) if keep else None, _p(n.c[t + 1]),
-                _p(n.hout[t]) if keep else None, C.c_void_p(n.xh[t + 1].data_ptr() + 4 * 256), 384, _p(n.w_head), _p(n.b_head), _p(n.out8[t]),
-                col(self.actions), C.c_void_p(forced.data_ptr() + 4 * a) if forced is not None else None, col(self.values), col(self.logp),
-                col(self.entropy), _p(self.logp_all[a]) if greedy else None, _p(self.rng_step), self.seed,
-                a | (2 if bootstrap else 0), int(greedy), E, st), lib)
+                _p(gates), _p(m.lstm.bias_ih), _p(m.lstm.bias_hh), row(n.c[t], H), row(n.act[t], 4 * H) if keep else None, row(n.c[t + 1], H),
+                row(n.hout[t], H) if keep else None, C.c_void_p(n.xh[t + 1].data_ptr() + 4 * (384 * e0 + 256)), 384, _p(n.w_head), _p(n.b_head),
+                row(n.out8[t], NOUT), col(self.actions), C.c_void_p(forced.data_ptr() + 4 * (2 * e0 + a)) if forced is not None else None,
+                col(self.values), col(self.logp), col(self.entropy), row(self.logp_all[a], 4) if greedy else None, _p(self.rng_step), self.seed,
+                a | (2 if bootstrap else 0), int(greedy), E, e0, st), lib)
         return self.actions[t]
 
     @torch.no_grad()

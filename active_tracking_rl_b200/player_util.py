@@ -79,6 +79,7 @@ class Agent(object):
     def clear_actions(self):
         self.values, self.log_probs, self.entropies, self.preds = [], [], [], []
         self.t = 0
+        self._prefetched = None  # (slot, bootstrap) of a forward the pipelined host path has already run for the next call
         return self
 
     # ---- episode / recurrent state ---------------------------------------------------------------
@@ -156,32 +157,16 @@ class Agent(object):
         eng = self.engine
         if forced_actions is not None:
             forced_actions = forced_actions.to(device=self.device, dtype=torch.int32).contiguous()
-        actions32 = eng.forward(t, forced=forced_actions)
+        if forced_actions is None and self._prefetched == (t, False):
+            actions32 = eng.actions[t]  # this step's forward already ran, slice by slice, while its observations were arriving
+        else:
+            actions32 = eng.forward(t, forced=forced_actions)
+        self._prefetched = None
         if host is None:
             self.env.step_into(actions32, self.obs_buf[t + 1], self.rew_buf[t], self.done_buf[t])
+            eng.post_step(t, self.done_buf[t])
         else:
-            host['actions'].copy_(actions32)  # D2H, synchronous
-            # the host round trip of the reference's data flow (player_util.py:54-59), pipelined: the env's D2H of observation chunk c + 1
-            # (library stream) overlaps the policy-side H2D of chunk c (this stream); PCIe is full duplex
-            C_ = int(host.get('chunks', 8))
-            self.env.step_host_begin(host['actions'], host['obs'], host['reward'], host['done'], C_)
-            f32 = host['obs'].dtype != torch.uint8
-            if f32 and getattr(self, '_obs_f32', None) is None:
-                self._obs_f32 = torch.empty(host['obs'].shape, dtype=torch.float32, device=self.device)
-            for c in range(C_):
-                lo, hi = self.env.chunk_bounds(c, C_)
-                self.env.host_chunk_wait(c)
-                if c == 0:
-                    self.rew_buf[t].copy_(host['reward'], non_blocking=True)
-                    self.done_buf[t].copy_(host['done'], non_blocking=True)
-                if hi <= lo:
-                    continue
-                if f32:  # float32 on the host side (the reference's dtype): upload, then narrow on the device (lossless: values 0, 1, 2, 4)
-                    self._obs_f32[lo:hi].copy_(host['obs'][lo:hi], non_blocking=True)
-                    self.obs_buf[t + 1, lo:hi].copy_(self._obs_f32[lo:hi])
-                else:
-                    self.obs_buf[t + 1, lo:hi].copy_(host['obs'][lo:hi], non_blocking=True)
-        eng.post_step(t, self.done_buf[t])
+            self._step_through_host(t, actions32, host)
         self.reward = self.rew_buf[t]
         self.done = self.done_buf[t]
         self.state = self.obs_buf[t + 1]
@@ -189,6 +174,53 @@ class Agent(object):
         self.last_actions = actions32
         self.t = t + 1
         return self
+
+    def _step_through_host(self, t, actions32, host):
+        """env.step through the host-buffer C ABI -- the host round trip of the reference's data flow (player_util.py:54-59) -- as a
+        three-stage pipeline over slices of consecutive envs: the env's D2H of observation chunk c + 1 (library stream), the re-upload
+        of chunk c (copy stream; PCIe is full duplex, the dependency is a device-side event) and, once the chunks of a slice of the
+        batch are back on the device, the NEXT policy step of that slice (this stream) while the rest is still on the bus.  The next
+        action_train / optimize call finds its forward done (`_prefetched`); the arithmetic is the whole-batch forward's, row for row."""
+        eng, env, dev = self.engine, self.env, self.device
+        host['actions'].copy_(actions32)  # D2H, synchronous
+        C_ = int(host.get('chunks', 8))
+        S_ = max(1, min(int(host.get('forward_slices', 2)), C_))
+        env.step_host_begin(host['actions'], host['obs'], host['reward'], host['done'], C_)
+        f32 = host['obs'].dtype != torch.uint8
+        if f32 and getattr(self, '_obs_f32', None) is None:
+            self._obs_f32 = torch.empty(host['obs'].shape, dtype=torch.float32, device=dev)
+        if getattr(self, '_copy_stream', None) is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        main, copy = torch.cuda.current_stream(dev), self._copy_stream
+        copy.wait_stream(main)  # the slots about to be overwritten are no longer read (previous rollout's backward, previous narrow)
+        landed, ev_flags = [], None
+        with torch.cuda.stream(copy):
+            for c in range(C_):
+                lo, hi = env.chunk_bounds(c, C_)
+                env.host_chunk_wait(c, on_stream=True)  # device-side dependency: the H2D engine trails the D2H engine by one chunk
+                if c == 0:
+                    self.rew_buf[t].copy_(host['reward'], non_blocking=True)
+                    self.done_buf[t].copy_(host['done'], non_blocking=True)
+                    ev_flags = copy.record_event()
+                if hi > lo:
+                    if f32:  # float32 on the host side (the reference's dtype): upload, then narrow on the device (lossless: values 0, 1, 2, 4)
+                        self._obs_f32[lo:hi].copy_(host['obs'][lo:hi], non_blocking=True)
+                        self.obs_buf[t + 1, lo:hi].copy_(self._obs_f32[lo:hi])
+                    else:
+                        self.obs_buf[t + 1, lo:hi].copy_(host['obs'][lo:hi], non_blocking=True)
+                if (c + 1) * S_ % C_ < S_:  # chunk c completes a forward slice
+                    landed.append((hi, copy.record_event()))
+        main.wait_event(ev_flags)
+        eng.post_step(t, self.done_buf[t])
+        prefetch = bool(host.get('prefetch', True)) and t + 1 <= eng.T
+        boot = t + 1 == eng.T  # slot T is the value-only forward of optimize (player_util.py:110-116)
+        first = 0
+        for hi, ev in landed:
+            main.wait_event(ev)
+            if prefetch and hi > first:
+                eng.forward(t + 1, bootstrap=boot, envs=(first, hi))
+                first = hi
+        self._prefetched = (t + 1, boot) if prefetch else None
 
     @property
     def fused(self):
@@ -305,7 +337,9 @@ class Agent(object):
         eng = self.engine
         if boot_forced_actions is not None:
             boot_forced_actions = boot_forced_actions.to(device=self.device, dtype=torch.int32).contiguous()
-        eng.forward(T, forced=boot_forced_actions, bootstrap=True)  # player_util.py:110-116 (it samples, like the reference)
+        if boot_forced_actions is not None or self._prefetched != (T, True):
+            eng.forward(T, forced=boot_forced_actions, bootstrap=True)  # player_util.py:110-116 (it samples, like the reference)
+        self._prefetched = None
         key = (float(self.args.entropy), float(self.w_entropy_target))
         optimizer.zero_grad()
         use_aux = 'reward' in self.args.aux

@@ -54,6 +54,9 @@ def make_parser():
     p.add_argument('--eval-every', type=int, default=0,
                    help='evaluate + checkpoint every this many updates on rank 0 (test.py:56-134); 0 = only once, at the end')
     p.add_argument('--graph', action='store_true', help='replay each iteration from a CUDA graph (Trainer.capture)')
+    p.add_argument('--plan-ahead', dest='plan_ahead', action='store_true',
+                   help='Maze / Nav ids: next-episode worlds (and Nav plans) are prepared on a side stream while the policy computes, '
+                        'so an auto-reset is a copy (same episodes: the RNG is counter-based)')
     p.add_argument('--max-grad-norm', type=float, default=0.0,
                    help='0 = the reference\'s effective behaviour (its clip_grad_norm_(params, 50) is inert); 50 = its intent')
     p.add_argument('--fp32-emulation', action='store_true', help='fp32 GEMMs through cuBLAS 12.9 BF16x9 emulation (see blas.py)')

@@ -151,6 +151,10 @@ int track2d_join(track2d_env *env, void *stream);
 int track2d_step_host_begin(track2d_env *env, const int32_t *actions_host, void *obs_host, int32_t obs_is_u8, float *reward_host,
                             uint8_t *done_host, int32_t n_chunks);
 int track2d_host_chunk_wait(track2d_env *env, int32_t chunk);
+/* Device-side form of the same dependency: work enqueued on `stream` after this call starts once chunk `chunk` has landed in the host
+ * buffers -- no host wake-up between a chunk's D2H and its consumer's H2D.  The host must not touch the buffers before it has
+ * synchronised with `stream` (or called track2d_host_chunk_wait). */
+int track2d_host_chunk_wait_stream(track2d_env *env, int32_t chunk, void *stream);
 
 /* ---- state read-back / injection (host pointers, synchronous; parity tests and the gym shim) -- */
 
@@ -275,12 +279,13 @@ int track2d_colsum(const float *x_dev, int64_t ld, int64_t M, int32_t N, float *
  * of the next step's GEMM; may be NULL), out8_dev [E][8] (may be NULL).  action_dev / forced_dev / value_dev / logp_dev /
  * entropy_dev address ONE COLUMN of [E][2] arrays (element stride 2).  The action is forced_dev's when given, the argmax when
  * `greedy` (player_util.py:69-82 action_test; logp_all_dev [E][4] then receives the log-probabilities, model.py:45-46), otherwise
- * a multinomial sample drawn with Philox4x32-10 keyed by `seed` at counter (row, rng_stream, *rng_step_dev). */
+ * a multinomial sample drawn with Philox4x32-10 keyed by `seed` at counter (first_row + row, rng_stream, *rng_step_dev): a batch
+ * processed in slices (pointers advanced to the slice, first_row = its first row) draws the same actions as the whole batch. */
 int track2d_lstm_heads_forward(const float *gates_dev, const float *b_ih_dev, const float *b_hh_dev, const float *c_prev_dev, float *act_dev,
                                float *c_next_dev, float *h_out_dev, float *h_next_dev, int64_t h_next_ld, const float *w_head_dev,
                                const float *b_head_dev, float *out8_dev, int32_t *action_dev, const int32_t *forced_dev, float *value_dev,
                                float *logp_dev, float *entropy_dev, float *logp_all_dev, const uint64_t *rng_step_dev, uint64_t seed,
-                               uint32_t rng_stream, int32_t greedy, int64_t E, void *stream);
+                               uint32_t rng_stream, int32_t greedy, int64_t E, int64_t first_row, void *stream);
 /* After env.step: envs whose done byte is set start the next step from zero recurrent state (train.py:73-74 -> Agent.reset):
  * zeroes their rows of h0 / h1 (row stride h_ld) and c0 / c1 ([E][128]); eps_len += 1 or = 0 (player_util.py:63,101); advances
  * the sampling counter.  Any pointer may be NULL. */

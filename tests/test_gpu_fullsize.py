@@ -157,6 +157,24 @@ def test_pipelined_host_step_equals_host_step(t2d, obs_dtype, n_chunks):
             assert torch.equal(hb["obs"][lo:hi], ha["obs"][lo:hi]), (t, c)
             if c == 0:
                 assert torch.equal(hb["reward"], ha["reward"]) and torch.equal(hb["done"], ha["done"])
+    # the device-side form of the chunk dependency (track2d_host_chunk_wait_stream): the re-upload of chunk c is ordered after its D2H
+    # by an event wait on the consumer's stream, the host never blocks in between
+    dev = torch.empty(hb["obs"].shape, dtype=obs_dtype, device="cuda")
+    for t in range(5):
+        acts = torch.from_numpy(rs.randint(0, 4, size=(E, 2)).astype(np.int32))
+        ha["actions"].copy_(acts)
+        hb["actions"].copy_(acts)
+        a.step_host(ha["actions"], ha["obs"], ha["reward"], ha["done"])
+        hb["obs"].fill_(77)
+        dev.fill_(55)
+        torch.cuda.synchronize()
+        b.step_host_begin(hb["actions"], hb["obs"], hb["reward"], hb["done"], n_chunks)
+        for c in range(n_chunks):
+            b.host_chunk_wait(c, on_stream=True)
+            lo, hi = b.chunk_bounds(c, n_chunks)
+            dev[lo:hi].copy_(hb["obs"][lo:hi], non_blocking=True)
+        torch.cuda.synchronize()
+        assert torch.equal(dev.cpu(), ha["obs"]) and torch.equal(hb["reward"], ha["reward"]) and torch.equal(hb["done"], ha["done"]), t
     assert a.status() == 0 and b.status() == 0
     a.close()
     b.close()

@@ -47,7 +47,7 @@ def test_lstm_heads_forward_matches_torch(lib, E, mode):
     off = lambda t: C.c_void_p(t.data_ptr() + 4 * col)  # noqa: E731
     _lib.check(lib.track2d_lstm_heads_forward(_p(gates), _p(b_ih), _p(b_hh), _p(c_prev), _p(act), _p(c_next), _p(h_out), C.c_void_p(xh_next.data_ptr() + 1024), 384,
                                               _p(w_head), _p(b_head), _p(out8), off(action), off(forced) if mode == "forced" else None, off(value), off(logp),
-                                              off(ent), _p(logp_all) if mode == "greedy" else None, _p(step), 1234, 1, int(mode == "greedy"), E, _stream()), lib)
+                                              off(ent), _p(logp_all) if mode == "greedy" else None, _p(step), 1234, 1, int(mode == "greedy"), E, 0, _stream()), lib)
     z = gates + b_ih + b_hh
     i, f, gg, o = z.chunk(4, 1)
     c2 = torch.sigmoid(f) * c_prev + torch.sigmoid(i) * torch.tanh(gg)
@@ -76,7 +76,7 @@ def test_lstm_heads_forward_matches_torch(lib, E, mode):
         action2 = torch.zeros_like(action)
         step.fill_(6)
         _lib.check(lib.track2d_lstm_heads_forward(_p(gates), _p(b_ih), _p(b_hh), _p(c_prev), None, _p(c_next), None, None, 384, _p(w_head), _p(b_head), None,
-                                                  off(action2), None, None, None, None, None, _p(step), 1234, 1, 0, E, _stream()), lib)
+                                                  off(action2), None, None, None, None, None, _p(step), 1234, 1, 0, E, 0, _stream()), lib)
         assert 0.3 < float((action2[:, col] != action[:, col]).float().mean()) < 0.9
 
 
@@ -332,3 +332,64 @@ def test_fused_sampling_trains_and_replays_as_a_cuda_graph():
     assert int(eng.rng_step.item()) == 34 * 20, int(eng.rng_step.item())
     assert tr.env.status() == 0
     tr.env.close()
+
+
+@pytest.mark.parametrize("network,E,slices", [("tat-maze-lstm", 50000, ((0, 24576), (24576, 50000))), ("maze-lstm", 50000, ((0, 25000), (25000, 50000))),
+                                              ("tat-maze-lstm", 1000, ((0, 304), (304, 305), (305, 1000)))])
+def test_forward_in_env_slices_equals_whole_batch_forward(network, E, slices):
+    """FusedA3C.forward(envs=(first, end)): every kernel is row-wise and the sampler's Philox counter is the env index, so the slices of
+    a batch add up to the whole-batch policy step, sampled actions included.  Bit for bit when the GEMM launch plan of the slices is the
+    whole batch's (>= 96 super-tiles: no split-K, which is the case of the pipelined host path at the bench sizes); with split-K the
+    reduction order over K differs and the values agree to rounding."""
+    from active_tracking_rl_b200.train import Trainer, default_args
+    T = 3
+    exact = E >= 49152
+    mk = lambda: Trainer(default_args(network=network, aux="reward" if "tat" in network else "none", num_envs=E, num_steps=T, seed=11), DEV)  # noqa: E731
+    ta, tb = mk(), mk()
+    ea, eb = ta.player.engine, tb.player.engine
+    same = (lambda x, y: torch.equal(x, y)) if exact else (lambda x, y: torch.allclose(x, y, rtol=1e-4, atol=1e-5))
+    for t in range(T):
+        ea.forward(t)
+        for lo, hi in slices:
+            eb.forward(t, envs=(lo, hi))
+        if exact:
+            assert torch.equal(ea.actions[t], eb.actions[t])
+        else:  # a probability that moved in the last bit can move a sample across its threshold: vanishingly rare
+            assert float((ea.actions[t] != eb.actions[t]).float().mean()) < 0.002
+            eb.actions[t].copy_(ea.actions[t])
+            eb.logp[t].copy_(ea.logp[t])
+        assert same(ea.values[t], eb.values[t]) and same(ea.logp[t], eb.logp[t]) and same(ea.entropy[t], eb.entropy[t])
+        for na, nb in zip(ea.nets, eb.nets):
+            assert same(na.xh[t + 1], nb.xh[t + 1]) and same(na.c[t + 1], nb.c[t + 1]) and same(na.out8[t], nb.out8[t])
+            assert same(na.act[t], nb.act[t]) and torch.equal(na.convout[t], nb.convout[t])
+        for tr in (ta, tb):
+            p = tr.player
+            p.env.step_into(p.engine.actions[t], p.obs_buf[t + 1], p.rew_buf[t], p.done_buf[t])
+            p.engine.post_step(t, p.done_buf[t])
+        assert torch.equal(ta.player.obs_buf[t + 1], tb.player.obs_buf[t + 1])
+    with pytest.raises(ValueError):
+        eb.forward(0, envs=(10, E + 1))
+    ta.env.close()
+    tb.env.close()
+
+
+@pytest.mark.parametrize("obs_dtype,chunks", [(torch.float32, 8), (torch.uint8, 4)])
+def test_pipelined_host_rollout_equals_device_rollout(obs_dtype, chunks):
+    """Agent.action_train(host=...): env.step through the host-buffer ABI with the next policy step started on the first half of the envs
+    while the second half's observations are still arriving -- same actions, rewards, statistics and updated weights, bit for bit, as
+    the device-resident rollout and as the host path without the prefetch"""
+    from active_tracking_rl_b200.train import Trainer, default_args
+    E, T = 50000, 5
+    mk = lambda: Trainer(default_args(num_envs=E, num_steps=T, seed=3), DEV)  # noqa: E731
+    ta, tb, tc = mk(), mk(), mk()
+    hb, hc = tb.env.alloc_host_buffers(obs_dtype=obs_dtype), tc.env.alloc_host_buffers(obs_dtype=obs_dtype)
+    hb["chunks"], hb["forward_slices"] = chunks, 2
+    hc["prefetch"] = False
+    for it in range(3):
+        sa, sb, sc = ta.iteration(), tb.iteration(host=hb), tc.iteration(host=hc)
+        for x, y, z in zip(sa, sb, sc):
+            assert torch.equal(x, y) and torch.equal(x, z), it
+        assert torch.equal(ta.optimizer.fp.flat, tb.optimizer.fp.flat) and torch.equal(ta.optimizer.fp.flat, tc.optimizer.fp.flat), it
+    assert ta.env.status() == 0 and tb.env.status() == 0 and tc.env.status() == 0
+    for tr in (ta, tb, tc):
+        tr.env.close()

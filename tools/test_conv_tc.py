@@ -12,6 +12,7 @@ from active_tracking_rl_b200 import _lib
 
 lib = _lib.load()
 what = sys.argv[1] if len(sys.argv) > 1 else "all"
+STRIDE = int(os.environ.get("X_STRIDE", "169"))
 DEV = "cuda:0"
 p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
 st = lambda: C.c_void_p(torch.cuda.current_stream().cuda_stream)  # noqa: E731
@@ -29,7 +30,13 @@ def make(N, seed):
 def fwd(obs, w1, b1, w2, b2):
     N = obs.shape[0]
     y = torch.empty(N, 512, device=DEV)
-    _lib.check(lib.track2d_maze_conv_forward_ex(p(obs), 1, 169, N, p(w1), p(b1), p(w2), p(b2), p(y), st()), lib)
+    if STRIDE != 169:  # the learner's layout: both agents' images interleaved, one agent's read with stride 338
+        wide = getattr(fwd, "_wide", None)
+        if wide is None or wide.shape[0] != N:
+            wide = fwd._wide = torch.zeros(N, STRIDE, device=DEV, dtype=torch.uint8)
+            wide[:, :169] = obs
+        obs = wide
+    _lib.check(lib.track2d_maze_conv_forward_ex(p(obs), 1, STRIDE, N, p(w1), p(b1), p(w2), p(b2), p(y), st()), lib)
     return y
 
 
