@@ -498,6 +498,10 @@ Plan make_plan(int64_t M, int64_t N, int64_t K) {
     if (K <= narrow_k && pl.sn == 2) pl.sn = 1;  // short reductions: 2x1 super-tiles keep the TMEM double buffer (epilogue overlap)
     pl.st_m = (tiles_m + pl.sm - 1) / pl.sm;
     pl.st_n = (tiles_n + pl.sn - 1) / pl.sn;
+    if (pl.sm == 2 && pl.sn == 2 && (int64_t)pl.st_m * pl.st_n < 96 && (int64_t)pl.st_m * tiles_n >= 96) {
+        pl.sn = 1;  // a medium-sized batch (a slice of the envs): 2x1 super-tiles fill the SMs without a split-K pass
+        pl.st_n = tiles_n;
+    }
     pl.nkb = (int)((K + BK - 1) / BK);
     const int64_t items = (int64_t)pl.st_m * pl.st_n;
     int64_t splits = items >= 96 ? 1 : (148 + items - 1) / items;  // fill the SMs when there are few super-tiles (weight gradients)

@@ -183,8 +183,10 @@ class Agent(object):
         action_train / optimize call finds its forward done (`_prefetched`); the arithmetic is the whole-batch forward's, row for row."""
         eng, env, dev = self.engine, self.env, self.device
         host['actions'].copy_(actions32)  # D2H, synchronous
-        C_ = int(host.get('chunks', 8))
-        S_ = max(1, min(int(host.get('forward_slices', 2)), C_))
+        C_ = int(host.get('chunks', 16))
+        S_ = host.get('forward_slices', 2)  # a count of equal slices, or the chunk counts at which a slice ends, e.g. (8, 12, 16)
+        ends = {(k + 1) * C_ // int(S_) for k in range(max(1, min(int(S_), C_)))} if isinstance(S_, int) else {int(k) for k in S_}
+        ends.add(C_)
         env.step_host_begin(host['actions'], host['obs'], host['reward'], host['done'], C_)
         f32 = host['obs'].dtype != torch.uint8
         if f32 and getattr(self, '_obs_f32', None) is None:
@@ -194,7 +196,7 @@ class Agent(object):
         main, copy = torch.cuda.current_stream(dev), self._copy_stream
         copy.wait_stream(main)  # the slots about to be overwritten are no longer read (previous rollout's backward, previous narrow)
         landed, ev_flags = [], None
-        with torch.cuda.stream(copy):
+        with torch.cuda.stream(copy):  # nothing but copies on this stream: the H2D engine never waits for a kernel
             for c in range(C_):
                 lo, hi = env.chunk_bounds(c, C_)
                 env.host_chunk_wait(c, on_stream=True)  # device-side dependency: the H2D engine trails the D2H engine by one chunk
@@ -203,23 +205,23 @@ class Agent(object):
                     self.done_buf[t].copy_(host['done'], non_blocking=True)
                     ev_flags = copy.record_event()
                 if hi > lo:
-                    if f32:  # float32 on the host side (the reference's dtype): upload, then narrow on the device (lossless: values 0, 1, 2, 4)
-                        self._obs_f32[lo:hi].copy_(host['obs'][lo:hi], non_blocking=True)
-                        self.obs_buf[t + 1, lo:hi].copy_(self._obs_f32[lo:hi])
-                    else:
-                        self.obs_buf[t + 1, lo:hi].copy_(host['obs'][lo:hi], non_blocking=True)
-                if (c + 1) * S_ % C_ < S_:  # chunk c completes a forward slice
+                    (self._obs_f32 if f32 else self.obs_buf[t + 1])[lo:hi].copy_(host['obs'][lo:hi], non_blocking=True)
+                if c + 1 in ends:  # chunk c completes a forward slice
                     landed.append((hi, copy.record_event()))
         main.wait_event(ev_flags)
         eng.post_step(t, self.done_buf[t])
-        prefetch = bool(host.get('prefetch', True)) and t + 1 <= eng.T
+        prefetch = bool(host.get('prefetch', True))
         boot = t + 1 == eng.T  # slot T is the value-only forward of optimize (player_util.py:110-116)
         first = 0
         for hi, ev in landed:
             main.wait_event(ev)
-            if prefetch and hi > first:
+            if hi <= first:
+                continue
+            if f32:  # float32 on the host side (the reference's dtype): narrowed on the device (lossless: the values are 0, 1, 2, 4)
+                self.obs_buf[t + 1, first:hi].copy_(self._obs_f32[first:hi])
+            if prefetch:
                 eng.forward(t + 1, bootstrap=boot, envs=(first, hi))
-                first = hi
+            first = hi
         self._prefetched = (t + 1, boot) if prefetch else None
 
     @property

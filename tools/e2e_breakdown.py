@@ -14,7 +14,8 @@ dt = torch.uint8 if (len(sys.argv) > 2 and sys.argv[2] == "u8") else torch.float
 tr = Trainer(default_args(num_envs=E), "cuda:0")
 host = tr.env.alloc_host_buffers(obs_dtype=dt)
 if os.environ.get("T2D_FWD_SLICES"):
-    host["forward_slices"] = int(os.environ["T2D_FWD_SLICES"])
+    v = os.environ["T2D_FWD_SLICES"]
+    host["forward_slices"] = int(v) if v.isdigit() else tuple(int(x) for x in v.split(","))
 if os.environ.get("T2D_CHUNKS"):
     host["chunks"] = int(os.environ["T2D_CHUNKS"])
 if os.environ.get("T2D_PREFETCH") == "0":
