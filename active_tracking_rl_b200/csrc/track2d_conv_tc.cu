@@ -491,8 +491,8 @@ constexpr int DZT_PITCH = 36;                       // floats per row of the sta
 constexpr int DZT_BYTES = 128 * DZT_PITCH * 4;
 // dy1s [img][pos][ic], scalar accesses (a conflict-free scalar store moves 128 bytes per LSU cycle, a 128-bit one half of that -- the
 // float4 layout was measured slower).  Bank of (img, pos, ic) = img offset + 18 pos + ic with the image offsets = {0, 1, 2, 3, 16, 17, 18,
-// 19} mod 32: the col2im lanes (8 images x 4 positions two apart: + {0, 4, 8, 12}) and the dW1 lanes (8 images x 4 channel quads:
-// + {0, 4, 8, 12}) both cover all 32 banks exactly once.
+// 19} mod 32: the col2im lanes (8 images x 4 positions two apart: + {0, 4, 8, 12}) and the dW1 lanes (warp = row; 8 images x 4 channel
+// quads: + {0, 4, 8, 12}) both cover all 32 banks exactly once.
 constexpr int DY_POS = 18, DY_IMG4 = 3600, DY_IMG1 = 897;
 __host__ __device__ constexpr int dy_img(int img) { return (img >> 2) * DY_IMG4 + (img & 3) * DY_IMG1; }
 static_assert(DY_IMG1 % 32 == 1 && DY_IMG4 % 32 == 16 && DY_IMG1 >= 49 * DY_POS && DY_IMG4 >= 4 * DY_IMG1, "dy1s banks");
@@ -677,7 +677,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) conv_tc_bwd_kernel(const XT *_
     } else if (warp >= C1_WARP0) {
         // ===== conv1 recompute (one tile ahead), then dz1 -> dW1 / db1 =====
         const int ct = threadIdx.x - C1_WARP0 * 32;
-        const int img = ct / 28, row = (ct % 28) >> 2, q = ct & 3;  // 7 warps = 8 images x 7 rows x 4 channel quads (28 = 0 mod 4)
+        const int row = ct >> 5, img = lane & 7, q = lane >> 3;  // warp = output row, lane = (image, channel quad): see the bank layout of dy1s
         // the conv1 weights are re-read from shared memory per tile: the registers hold the 40 gradient accumulators
         float aw1[4][9], ab1[4];
 #pragma unroll
@@ -780,7 +780,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) conv_tc_bwd_kernel(const XT *_
             const int ch = ct / 10, k = ct - ch * 10, qq = ch >> 2, c = ch & 3;
             float t = 0.f;
             for (int im = 0; im < 8; ++im)
-                for (int rw = 0; rw < 7; ++rw) t += red[(im * 28 + rw * 4 + qq) * 40 + c * 10 + k];
+                for (int rw = 0; rw < 7; ++rw) t += red[(rw * 32 + qq * 8 + im) * 40 + c * 10 + k];
             if (k < 9) my_part[32 * 144 + ch * 9 + k] = t;
             else my_part[32 * 144 + 144 + ch] = t;
         }

@@ -183,8 +183,11 @@ class Agent(object):
         action_train / optimize call finds its forward done (`_prefetched`); the arithmetic is the whole-batch forward's, row for row."""
         eng, env, dev = self.engine, self.env, self.device
         host['actions'].copy_(actions32)  # D2H, synchronous
-        C_ = int(host.get('chunks', 16))
-        S_ = host.get('forward_slices', 2)  # a count of equal slices, or the chunk counts at which a slice ends, e.g. (8, 12, 16)
+        # defaults by batch size: ~2 MB per transfer chunk (a small batch is bound by launches, not by the bus: one chunk, one slice);
+        # two forward slices once half a batch still fills the GPU (>= 96 GEMM super-tiles of 256 rows)
+        obs_bytes = host['obs'].numel() * host['obs'].element_size()
+        C_ = int(host.get('chunks', max(1, min(16, obs_bytes // (2 << 20)))))
+        S_ = host.get('forward_slices', 2 if self.num_envs >= 2 * 96 * 256 else 1)  # a count of equal slices, or the chunk counts at which a slice ends, e.g. (8, 12, 16)
         ends = {(k + 1) * C_ // int(S_) for k in range(max(1, min(int(S_), C_)))} if isinstance(S_, int) else {int(k) for k in S_}
         ends.add(C_)
         env.step_host_begin(host['actions'], host['obs'], host['reward'], host['done'], C_)
