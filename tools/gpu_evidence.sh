@@ -1,3 +1,4 @@
+# gpurun payload that regenerates the evidence under profiles/: bench lines of configs 2, 3, 5, the per-launch list under graph replay, one ncu --set full of the conv backward
 cd $GRAFT_REPO_ROOT
 timeout 600 python bench.py > gpurun_out/bench_r2_final.json 2> gpurun_out/bench_r2_final.err; tail -c 300 gpurun_out/bench_r2_final.err
 timeout 400 python bench.py --config 2 --no-cpu-baseline > gpurun_out/bench_r2_final_config2.json 2> gpurun_out/bench_cfg2.err

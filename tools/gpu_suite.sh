@@ -1,3 +1,4 @@
+# gpurun payload: forward-conv microbench, the whole GPU test suite, the default bench line (gpurun -- "bash tools/gpu_suite.sh")
 cd $GRAFT_REPO_ROOT
 timeout 300 python tools/test_conv_tc.py fwd 2>&1 | tail -3
 timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -15
