@@ -334,7 +334,7 @@ class Track1v1Env(object):
         if len(action) < 2:
             raise TypeError("step() needs one action per agent")
         a = self._host['actions']
-        a[0, 0], a[0, 1] = int(action[0]), int(action[1])
+        a[0, 0], a[0, 1] = (int(np.asarray(x).reshape(-1)[0]) for x in action[:2])  # scalars, 0-d or 1-element arrays, as gym callers pass them
         self.vec.step_host(a, self._host['obs'], self._host['reward'], self._host['done'])
         rewards = self.vec.get_rewards_f64()[0]
         st = self.state
