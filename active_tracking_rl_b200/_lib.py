@@ -81,6 +81,14 @@ SYMBOLS = {
     "track2d_policy_post_step": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp]),
     "track2d_embed_add": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _i32, _i64, _vp]),
     "track2d_a3c_loss_grad": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _dbl, _dbl, _dbl, _dbl, _dbl, _i32, _i32, _i32, _vp]),
+    "track2d_peer_create": (C.c_int, [_i32, _i32, _i64, _i32, C.POINTER(C.c_void_p)]),
+    "track2d_peer_handle": (C.c_int, [_vp, _vp]),
+    "track2d_peer_connect": (C.c_int, [_vp, _vp]),
+    "track2d_peer_segment": (C.c_int, [_vp, C.POINTER(C.c_void_p)]),
+    "track2d_peer_connect_local": (C.c_int, [_vp, C.POINTER(C.c_void_p)]),
+    "track2d_peer_allreduce": (C.c_int, [_vp, _vp, _vp]),
+    "track2d_peer_status": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
+    "track2d_peer_destroy": (None, [_vp]),
     "track2d_lstm_heads_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "track2d_relu_backward_workspace_floats": (C.c_int64, [_i64, _i32]),
     "track2d_relu_backward_groupsum": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _i64, _vp]),

@@ -10,6 +10,7 @@ SharedAdam update (so the replicas stay bit-identical without ever broadcasting 
 """
 import argparse
 import os
+import sys
 import time
 
 import torch
@@ -105,9 +106,25 @@ class Trainer(object):
         self.player.reset()
         self.n_iter = 0
         self.allreduce = None
+        self.peer = None  # all-reduce over NVLink peer memory (peer.PeerAllReduce): plain kernels, capturable with the iteration
         if world_size > 1:
             import torch.distributed as dist
             self.allreduce = lambda g: dist.all_reduce(g, op=dist.ReduceOp.SUM)
+            if self.device.type == 'cuda' and world_size <= 8 and os.environ.get("T2D_PEER_ALLREDUCE", "1") != "0":
+                ok = 1
+                try:
+                    from .peer import PeerAllReduce
+                    self.peer = PeerAllReduce(self.optimizer.fp.grad.numel(), self.device, rank, world_size)
+                except Exception as ex:  # noqa: BLE001  (no peer access / IPC on this box: the library collective does it)
+                    ok = 0
+                    sys.stderr.write("rank %d: peer-memory all-reduce unavailable (%s); using torch.distributed\n" % (rank, str(ex).splitlines()[0] if str(ex) else repr(ex)))
+                flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN)  # every rank takes the same path
+                if int(flag.item()) == 1:
+                    self.allreduce = self.peer
+                elif self.peer is not None:
+                    self.peer.close()
+                    self.peer = None
 
     def iteration(self, training_mode=None, host=None):
         """train.py:69-95 for all envs: detach LSTM state, num_steps x (policy.step, env.step), optimize.
@@ -142,7 +159,7 @@ class Trainer(object):
         step0, iter0, nsteps0 = self.optimizer.step_count, self.n_iter, self.player.n_steps
         l0 = self.env.lib.track2d_launch_count()
         self._graph_apply = None
-        if self.world_size == 1:
+        if self.world_size == 1 or self.peer is not None:  # the peer-memory all-reduce is ordinary kernels: one graph on any number of GPUs
             with torch.cuda.graph(self._graph, stream=side):
                 self._graph_out = self.iteration(mode)
         elif os.environ.get("T2D_NCCL_IN_GRAPH", "0") == "1":

@@ -318,6 +318,23 @@ int64_t track2d_relu_backward_workspace_floats(int64_t M, int32_t N);
 int track2d_relu_backward_groupsum(float *dy_dev, const float *y_dev, int64_t y_ld, const int32_t *group_dev, int64_t M, int32_t N,
                                    float *dbias_dev, float *gw_dev, float *gb_dev, float *workspace_dev, int64_t workspace_floats, void *stream);
 
+/* ---- gradient all-reduce over NVLink / NVSwitch peer memory (csrc/track2d_peer.cu) -------------------------------------------
+ * Reference: main.py:102-116 + utils.py:36-44 (ensure_shared_grads): the W workers' gradients meet in one shared model.  Here every
+ * GPU applies the same update to the sum of all ranks' flat fp32 gradients; this is that sum, as plain kernels on the caller's
+ * stream (CUDA-graph capturable), reading the peers' copies directly: grad[i] = sum over ranks 0..world-1, in that order, of the
+ * peers' grad[i] -- the same bits on every rank.  One process per GPU: create, exchange the 64-byte handles (any transport),
+ * connect, then call track2d_peer_allreduce once per update on EVERY rank.  Waits for a peer are bounded; a peer that never arrives is
+ * reported by track2d_peer_status (0 = ok) instead of hanging the device.  world <= 8. */
+typedef struct track2d_peer track2d_peer;
+int track2d_peer_create(int32_t rank, int32_t world, int64_t n_floats, int32_t device, track2d_peer **out);
+int track2d_peer_handle(track2d_peer *p, uint8_t *handle64_out);                 /* cudaIpcGetMemHandle of this rank's segment */
+int track2d_peer_connect(track2d_peer *p, const uint8_t *handles_world_x_64);    /* all ranks' handles, rank-major */
+int track2d_peer_segment(track2d_peer *p, void **segment_out);                   /* same-process peers: the raw segment pointer ... */
+int track2d_peer_connect_local(track2d_peer *p, void *const *segments_world);    /* ... and a connect that takes them (tests) */
+int track2d_peer_allreduce(track2d_peer *p, float *grad_dev, void *stream);      /* in place; grad_dev 16-byte aligned, n_floats long */
+int track2d_peer_status(track2d_peer *p, uint64_t *status_out);
+void track2d_peer_destroy(track2d_peer *p);
+
 #ifdef __cplusplus
 }
 #endif
