@@ -1,8 +1,8 @@
 """The synchronous on-device actor-learner that replaces the reference's W Hogwild worker processes
 (main.py:102-116, train.py:15-113): E envs per GPU advance in lock step -- policy.step and env.step
 alternate on one CUDA stream with no host round trip -- and every num_steps steps ONE update is applied.
-Across GPUs (one process each) the env shards are independent; the only exchange is one NCCL
-all-reduce of the flat gradient per rollout, after which every rank applies the identical fused
+Across GPUs (one process each) the env shards are independent; the only exchange is one all-reduce of
+the flat gradient per rollout (over NVLink peer memory, peer.py; NCCL as the fallback), after which every rank applies the identical fused
 SharedAdam update (so the replicas stay bit-identical without ever broadcasting weights again).
 
     python -m active_tracking_rl_b200.train --env Track2D-BlockPartialPZR-v0 --num-envs 65536 --iters 100
@@ -141,7 +141,7 @@ class Trainer(object):
     # ---- CUDA-graph replay of the whole iteration ------------------------------------------------------------
     def capture(self, training_mode=None, warmup=3):
         """Capture one full iteration -- 20 x (policy forward, env.step, auto-reset), bootstrap, GAE, losses, backward,
-        [NCCL all-reduce], fused SharedAdam -- into ONE CUDA graph.  A rollout is ~4,300 kernel launches; below
+        [gradient all-reduce over peer memory], fused SharedAdam -- into ONE CUDA graph.  A rollout is ~4,300 kernel launches; below
         ~16k envs per GPU the Python/driver launch path, not the GPU, bounds the step, and a graph replay removes it.
         Everything inside is already stream-ordered with static shapes and no host synchronisation (the env kernels
         are plain launches on the capturing stream), which is what makes the capture legal."""
