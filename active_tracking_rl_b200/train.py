@@ -262,6 +262,8 @@ def main():
         if tr.n_iter > args.max_step:  # test.py:130-134
             break
     evaluate()
+    if tr.peer is not None and tr.peer.status():  # a peer's signal did not arrive within the bound: the gradient sums cannot be trusted
+        raise RuntimeError("rank %d: peer-memory all-reduce timed out waiting for rank %d" % (rank, tr.peer.status() - 1))
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
