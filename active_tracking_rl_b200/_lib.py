@@ -87,6 +87,7 @@ SYMBOLS = {
     "track2d_peer_segment": (C.c_int, [_vp, C.POINTER(C.c_void_p)]),
     "track2d_peer_connect_local": (C.c_int, [_vp, C.POINTER(C.c_void_p)]),
     "track2d_peer_allreduce": (C.c_int, [_vp, _vp, _vp]),
+    "track2d_peer_sharedadam_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _dbl, _dbl, _dbl, _dbl, _dbl, _vp, _vp, _vp]),
     "track2d_peer_status": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "track2d_peer_destroy": (None, [_vp]),
     "track2d_lstm_heads_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),

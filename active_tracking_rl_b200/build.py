@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libtrack2d.so")
 SOURCES = ["track2d_api.cu", "track2d_step.cu", "track2d_reset.cu", "track2d_optim.cu", "track2d_policy.cu", "track2d_gemm.cu", "track2d_lstm.cu", "track2d_a3c.cu", "track2d_conv_tc.cu", "track2d_peer.cu"]
-HEADERS = ["track2d_common.cuh", "track2d_nav.cuh", "track2d_tc.cuh", os.path.join("..", "..", "include", "track2d.h")]
+HEADERS = ["track2d_common.cuh", "track2d_nav.cuh", "track2d_tc.cuh", "track2d_adam.cuh", os.path.join("..", "..", "include", "track2d.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -12,6 +12,7 @@
 #include <stdint.h>
 
 #include "../../include/track2d.h"
+#include "track2d_adam.cuh"
 
 namespace {
 
@@ -48,14 +49,6 @@ __global__ void adam_prep_kernel(long long *step_dev, float *neg_step_out, doubl
         double bc1 = 1.0 - pow(beta1, (double)t), bc2 = 1.0 - pow(beta2, (double)t);
         *neg_step_out = (float)(-(lr * sqrt(bc2) / bc1));
     }
-}
-
-__device__ __forceinline__ void adam_one(float &p, float g, float &m, float &v, float &vmax, float b1, float b2, float eps, float neg_step) {
-    m = m * b1 + (1.f - b1) * g;
-    v = v * b2 + (1.f - b2) * g * g;
-    vmax = fmaxf(vmax, v);
-    float denom = sqrtf(vmax) + eps;
-    p = p + (neg_step * m) / denom;
 }
 
 __global__ void __launch_bounds__(256) sharedadam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m,
@@ -120,6 +113,18 @@ __global__ void __launch_bounds__(256) gae_kernel(const float *__restrict__ rewa
 
 void t2d_set_error(const char *fmt, ...);
 void t2d_count_launches(int n);
+
+void t2d_preload_optim_kernels() {  // see track2d_peer_create: kernels that may be launched next to a waiting kernel are loaded up front
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, adam_prep_kernel);
+    cudaFuncGetAttributes(&fa, sharedadam_kernel);
+    cudaFuncGetAttributes(&fa, sqnorm_kernel);
+}
+
+cudaError_t t2d_launch_adam_prep(long long *step_dev, float *neg_step_out, double lr, double beta1, double beta2, cudaStream_t s) {
+    adam_prep_kernel<<<1, 32, 0, s>>>(step_dev, neg_step_out, lr, beta1, beta2);
+    return cudaGetLastError();
+}
 
 extern "C" int track2d_sharedadam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, float *max_exp_avg_sq,
                                        int64_t n, int64_t step, double lr, double beta1, double beta2, double eps, double max_grad_norm,

@@ -22,6 +22,7 @@
 #include <string.h>
 
 #include "../../include/track2d.h"
+#include "track2d_adam.cuh"
 
 void t2d_set_error(const char *fmt, ...);
 void t2d_count_launches(int n);
@@ -121,6 +122,54 @@ __global__ void __launch_bounds__(256) peer_sum_kernel(PeerTable t, float *__res
     }
 }
 
+// (4) + (5) + the update: the exchange and SharedAdam.step in ONE kernel -- every thread adds up the ranks' gradients for its four
+// parameters (same order everywhere), leaves the sum in `grad` (what an all-reduce would have left) and applies the update
+__global__ void __launch_bounds__(256) peer_sum_adam_kernel(PeerTable t, float *__restrict__ grad, float *__restrict__ param, float *__restrict__ m,
+                                                            float *__restrict__ v, float *__restrict__ vmax, long long n, float b1, float b2, float eps,
+                                                            float grad_scale, const float *__restrict__ neg_step_dev, unsigned int *__restrict__ ticket) {
+    const float neg_step = *neg_step_dev;
+    const long long stride = (long long)gridDim.x * blockDim.x * 4;
+    for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+        if (i + 3 < n) {
+            float4 G = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int p = 0; p < t.world; ++p) {
+                const float4 x = __ldcv(reinterpret_cast<const float4 *>(t.data[p] + i));
+                G.x += x.x; G.y += x.y; G.z += x.z; G.w += x.w;
+            }
+            *reinterpret_cast<float4 *>(grad + i) = G;
+            float4 P = *reinterpret_cast<float4 *>(param + i), M = *reinterpret_cast<float4 *>(m + i), V = *reinterpret_cast<float4 *>(v + i),
+                   X = *reinterpret_cast<float4 *>(vmax + i);
+            adam_one(P.x, G.x * grad_scale, M.x, V.x, X.x, b1, b2, eps, neg_step);
+            adam_one(P.y, G.y * grad_scale, M.y, V.y, X.y, b1, b2, eps, neg_step);
+            adam_one(P.z, G.z * grad_scale, M.z, V.z, X.z, b1, b2, eps, neg_step);
+            adam_one(P.w, G.w * grad_scale, M.w, V.w, X.w, b1, b2, eps, neg_step);
+            *reinterpret_cast<float4 *>(param + i) = P;
+            *reinterpret_cast<float4 *>(m + i) = M;
+            *reinterpret_cast<float4 *>(v + i) = V;
+            *reinterpret_cast<float4 *>(vmax + i) = X;
+        } else {
+            for (long long j = i; j < n; ++j) {
+                float g = 0.f;
+                for (int p = 0; p < t.world; ++p) g += __ldcv(t.data[p] + j);
+                grad[j] = g;
+                adam_one(param[j], g * grad_scale, m[j], v[j], vmax[j], b1, b2, eps, neg_step);
+            }
+        }
+    }
+    __shared__ bool last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+        if (last) *ticket = 0u;
+    }
+    __syncthreads();
+    if (last && threadIdx.x < t.world && (int)threadIdx.x != t.rank) {
+        const unsigned long long e = t.flags[t.rank]->epoch;
+        st_release_sys(&t.flags[threadIdx.x]->done[t.rank], e);
+    }
+}
+
 }  // namespace
 
 struct track2d_peer {
@@ -175,6 +224,8 @@ extern "C" int track2d_peer_create(int32_t rank, int32_t world, int64_t n_floats
         cudaFuncGetAttributes(&fa, peer_wait_done_kernel);
         cudaFuncGetAttributes(&fa, peer_ready_kernel);
         cudaFuncGetAttributes(&fa, peer_sum_kernel);
+        cudaFuncGetAttributes(&fa, peer_sum_adam_kernel);
+        t2d_preload_optim_kernels();
     }
     p->table.rank = rank; p->table.world = world;
     set_entry(p, rank, p->seg);
@@ -243,6 +294,42 @@ extern "C" int track2d_peer_allreduce(track2d_peer *p, float *grad_dev, void *st
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail("track2d_peer_allreduce", e);
     t2d_count_launches(3);
+    return T2D_OK;
+}
+
+// The exchange fused with the update it feeds: same result, bit for bit, as track2d_peer_allreduce followed by track2d_sharedadam_step
+// (without clipping -- a global gradient norm needs the whole sum first), in one launch less and without re-reading the summed gradient.
+extern "C" int track2d_peer_sharedadam_step(track2d_peer *p, float *param, float *grad, float *exp_avg, float *exp_avg_sq, float *max_exp_avg_sq,
+                                            double lr, double beta1, double beta2, double eps, double grad_scale, float *norm_scratch,
+                                            int64_t *step_dev, void *stream) {
+    if (!p || !param || !grad || !exp_avg || !exp_avg_sq || !max_exp_avg_sq || !norm_scratch || !step_dev ||
+        ((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq | (uintptr_t)max_exp_avg_sq) & 15u) != 0)) {
+        t2d_set_error("track2d_peer_sharedadam_step: bad argument (16-byte aligned buffers, device-resident step counter)");
+        return T2D_E_INVALID;
+    }
+    if (!p->connected) { t2d_set_error("track2d_peer_sharedadam_step: call track2d_peer_connect first"); return T2D_E_STATE; }
+    Guard g(p->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaSuccess;
+    if (p->world > 1) {
+        peer_wait_done_kernel<<<1, 32, 0, st>>>(p->table);
+        e = cudaMemcpyAsync(p->seg, grad, (size_t)p->n * 4, cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) return cuda_fail("track2d_peer_sharedadam_step", e);
+        peer_ready_kernel<<<1, 32, 0, st>>>(p->table);
+    } else {
+        e = cudaMemcpyAsync(p->seg, grad, (size_t)p->n * 4, cudaMemcpyDeviceToDevice, st);  // world 1: the "sum" of one copy
+        if (e != cudaSuccess) return cuda_fail("track2d_peer_sharedadam_step", e);
+    }
+    e = t2d_launch_adam_prep(reinterpret_cast<long long *>(step_dev), norm_scratch + 1, lr, beta1, beta2, st);
+    if (e != cudaSuccess) return cuda_fail("track2d_peer_sharedadam_step", e);
+    long long blocks = (p->n / 4 + 255) / 256;
+    if (blocks > 296) blocks = 296;
+    if (blocks < 1) blocks = 1;
+    peer_sum_adam_kernel<<<(int)blocks, 256, 0, st>>>(p->table, grad, param, exp_avg, exp_avg_sq, max_exp_avg_sq, p->n, (float)beta1, (float)beta2,
+                                                      (float)eps, (float)grad_scale, norm_scratch + 1, p->ticket);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail("track2d_peer_sharedadam_step", e);
+    t2d_count_launches(p->world > 1 ? 4 : 2);
     return T2D_OK;
 }
 

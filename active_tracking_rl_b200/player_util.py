@@ -358,9 +358,16 @@ class Agent(object):
         """second half of optimize(): [all-reduce of the flat gradient], [clip] + SharedAdam, and the hand-over of observation /
         recurrent state to the next rollout.  Split off so that a multi-GPU run can replay the two halves as CUDA graphs with the
         NCCL all-reduce launched eagerly between them."""
+        fused_exchange = None
         if allreduce is not None and world_size > 1 and not skip_allreduce:
-            allreduce(optimizer.fp.grad)
-        optimizer.step(max_grad_norm=self.max_grad_norm, grad_scale=1.0 / world_size)
+            if hasattr(allreduce, 'h') and hasattr(optimizer, 'fp'):  # peer.PeerAllReduce: the exchange rides in the optimizer kernel
+                fused_exchange = allreduce
+            else:
+                allreduce(optimizer.fp.grad)
+        if fused_exchange is not None:
+            optimizer.step(max_grad_norm=self.max_grad_norm, grad_scale=1.0 / world_size, peer=fused_exchange)
+        else:
+            optimizer.step(max_grad_norm=self.max_grad_norm, grad_scale=1.0 / world_size)
         if self.engine is not None:
             T = self.t
             self.engine.mark_dirty()

@@ -74,15 +74,25 @@ class SharedAdam(object):
     def zero_grad(self):
         self.fp.zero_grad()
 
-    def step(self, max_grad_norm=50.0, grad_scale=1.0):
+    def step(self, max_grad_norm=50.0, grad_scale=1.0, peer=None):
+        """one update.  peer (peer.PeerAllReduce): the gradient is first summed over the ranks -- inside the SAME kernel when there is no
+        clipping (track2d_peer_sharedadam_step), else by peer(grad) followed by the plain step; fp.grad holds the sum afterwards"""
         self.step_count += 1
         dev = self.fp.flat.device
         p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         with _lib.on_device(dev):
+            if peer is not None and not (max_grad_norm and max_grad_norm > 0):
+                _lib.check(self.lib.track2d_peer_sharedadam_step(
+                    peer.h, p(self.fp.flat), p(self.fp.grad), p(self.exp_avg), p(self.exp_avg_sq), p(self.max_exp_avg_sq), self.lr,
+                    self.betas[0], self.betas[1], self.eps, float(grad_scale), p(self.norm_scratch), p(self.step_dev), st), self.lib)
+                return
+            if peer is not None:
+                peer(self.fp.grad)
             _lib.check(self.lib.track2d_sharedadam_step(
                 p(self.fp.flat), p(self.fp.grad), p(self.exp_avg), p(self.exp_avg_sq), p(self.max_exp_avg_sq), self.fp.numel,
                 self.step_count, self.lr, self.betas[0], self.betas[1], self.eps, float(max_grad_norm or 0.0), float(grad_scale),
-                p(self.norm_scratch), p(self.step_dev), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), self.lib)
+                p(self.norm_scratch), p(self.step_dev), st), self.lib)
 
     def advance_for_replay(self):
         """a CUDA-graph replay of step() advances the device counter by itself; keep the host mirror in sync"""

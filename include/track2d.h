@@ -332,6 +332,12 @@ int track2d_peer_connect(track2d_peer *p, const uint8_t *handles_world_x_64);   
 int track2d_peer_segment(track2d_peer *p, void **segment_out);                   /* same-process peers: the raw segment pointer ... */
 int track2d_peer_connect_local(track2d_peer *p, void *const *segments_world);    /* ... and a connect that takes them (tests) */
 int track2d_peer_allreduce(track2d_peer *p, float *grad_dev, void *stream);      /* in place; grad_dev 16-byte aligned, n_floats long */
+/* The exchange FUSED with the update it feeds (one kernel sums the ranks' gradients and applies SharedAdam.step, shared_optim.py:122-175):
+ * bit for bit track2d_peer_allreduce followed by track2d_sharedadam_step with max_grad_norm = 0 and the device-resident counter
+ * (clipping needs the global norm of the whole sum first -- use the two calls then).  grad_dev ends up holding the sum. */
+int track2d_peer_sharedadam_step(track2d_peer *p, float *param, float *grad_dev, float *exp_avg, float *exp_avg_sq, float *max_exp_avg_sq,
+                                 double lr, double beta1, double beta2, double eps, double grad_scale, float *norm_scratch,
+                                 int64_t *step_dev, void *stream);
 int track2d_peer_status(track2d_peer *p, uint64_t *status_out);
 void track2d_peer_destroy(track2d_peer *p);
 

@@ -67,6 +67,50 @@ def test_peer_allreduce_is_graph_capturable():
         p.close()
 
 
+@pytest.mark.parametrize("world", [2, 3])
+def test_fused_exchange_and_update_equals_allreduce_then_step(world):
+    """track2d_peer_sharedadam_step == track2d_peer_allreduce + track2d_sharedadam_step, bit for bit, over several updates (the
+    device-resident counter, AMSGrad state and the summed gradient left in grad included)"""
+    from active_tracking_rl_b200.peer import PeerAllReduce
+    from active_tracking_rl_b200.shared_optim import SharedAdam
+    dev = torch.device("cuda:0")
+    n = 70_001
+    g = torch.Generator(device=dev).manual_seed(5)
+    init = torch.randn(n, generator=g, device=dev)
+
+    def make_side():
+        params = [torch.nn.Parameter(init.clone())]
+        opts = [SharedAdam([torch.nn.Parameter(init.clone())], lr=1e-3, amsgrad=True) for _ in range(world)]
+        peers = [PeerAllReduce(opts[0].fp.numel, dev, r, world, connect=False) for r in range(world)]
+        segs = [p.segment() for p in peers]
+        for p in peers:
+            p.connect_local(segs)
+        del params
+        return opts, peers
+
+    (oa, pa), (ob, pb) = make_side(), make_side()
+    streams = [torch.cuda.Stream(device=dev) for _ in range(world)]
+    for it in range(4):
+        grads = [torch.randn(oa[0].fp.numel, generator=g, device=dev) for _ in range(world)]
+        for r in range(world):
+            oa[r].fp.grad.copy_(grads[r])
+            ob[r].fp.grad.copy_(grads[r])
+        torch.cuda.synchronize()
+        for r in range(world):
+            with torch.cuda.stream(streams[r]):
+                pa[r](oa[r].fp.grad)                                        # exchange, then the plain update
+                oa[r].step(max_grad_norm=0.0, grad_scale=1.0 / world)
+                ob[r].step(max_grad_norm=0.0, grad_scale=1.0 / world, peer=pb[r])  # both in one kernel
+        torch.cuda.synchronize()
+        for r in range(world):
+            assert torch.equal(oa[r].fp.flat, ob[r].fp.flat) and torch.equal(oa[r].fp.grad, ob[r].fp.grad), (it, r)
+            assert torch.equal(oa[r].max_exp_avg_sq, ob[r].max_exp_avg_sq) and torch.equal(oa[r].step_dev, ob[r].step_dev)
+            assert torch.equal(ob[r].fp.flat, ob[0].fp.flat)  # replicas identical
+    assert all(p.status() == 0 for p in pa + pb)
+    for p in pa + pb:
+        p.close()
+
+
 def _worker(rank, world, port, out):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
