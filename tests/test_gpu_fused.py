@@ -373,6 +373,22 @@ def test_forward_in_env_slices_equals_whole_batch_forward(network, E, slices):
     tb.env.close()
 
 
+def test_host_rollout_of_a_small_batch_equals_device_rollout():
+    """the defaults of the host path for a small batch (one transfer chunk, the prefetched policy step over the whole batch)"""
+    from active_tracking_rl_b200.train import Trainer, default_args
+    mk = lambda: Trainer(default_args(num_envs=1003, num_steps=5, seed=4), DEV)  # noqa: E731
+    ta, tb = mk(), mk()
+    hb = tb.env.alloc_host_buffers(obs_dtype=torch.float32)
+    for it in range(3):
+        sa, sb = ta.iteration(), tb.iteration(host=hb)
+        for x, y in zip(sa, sb):
+            assert torch.equal(x, y), it
+        assert torch.equal(ta.optimizer.fp.flat, tb.optimizer.fp.flat), it
+    assert ta.env.status() == 0 and tb.env.status() == 0
+    ta.env.close()
+    tb.env.close()
+
+
 @pytest.mark.parametrize("obs_dtype,chunks", [(torch.float32, 8), (torch.uint8, 4)])
 def test_pipelined_host_rollout_equals_device_rollout(obs_dtype, chunks):
     """Agent.action_train(host=...): env.step through the host-buffer ABI with the next policy step started on the first half of the envs
