@@ -15,6 +15,26 @@ import torch
 from . import _lib, learner
 
 
+def host_pipeline_plan(num_envs, obs_bytes, chunks=None, forward_slices=None):
+    """(number of transfer chunks, set of chunk counts after which a forward slice starts) of Agent._step_through_host.
+    Defaults by batch size: ~2 MB per transfer chunk, at most 16 (a small batch is bound by launches, not by the bus: one chunk); two
+    forward slices once half a batch still fills the GPU (>= 96 GEMM super-tiles of 256 rows), else one.  forward_slices: a count of
+    equal slices, or the chunk counts at which a slice ends, e.g. (8, 12, 16)."""
+    C_ = int(chunks) if chunks is not None else max(1, min(16, int(obs_bytes) // (2 << 20)))
+    if not 1 <= C_ <= 16:
+        raise ValueError("host pipeline: 1..16 transfer chunks")
+    S_ = forward_slices if forward_slices is not None else (2 if num_envs >= 2 * 96 * 256 else 1)
+    if isinstance(S_, int):
+        n = max(1, min(S_, C_))
+        ends = {(k + 1) * C_ // n for k in range(n)}
+    else:
+        ends = {int(k) for k in S_}
+        if not ends or min(ends) < 1 or max(ends) > C_:
+            raise ValueError("host pipeline: slice boundaries are chunk counts in 1..%d" % C_)
+    ends.add(C_)
+    return C_, ends
+
+
 class Agent(object):
     def __init__(self, model, env, args, state, device):
         self.model = model
@@ -183,13 +203,7 @@ class Agent(object):
         action_train / optimize call finds its forward done (`_prefetched`); the arithmetic is the whole-batch forward's, row for row."""
         eng, env, dev = self.engine, self.env, self.device
         host['actions'].copy_(actions32)  # D2H, synchronous
-        # defaults by batch size: ~2 MB per transfer chunk (a small batch is bound by launches, not by the bus: one chunk, one slice);
-        # two forward slices once half a batch still fills the GPU (>= 96 GEMM super-tiles of 256 rows)
-        obs_bytes = host['obs'].numel() * host['obs'].element_size()
-        C_ = int(host.get('chunks', max(1, min(16, obs_bytes // (2 << 20)))))
-        S_ = host.get('forward_slices', 2 if self.num_envs >= 2 * 96 * 256 else 1)  # a count of equal slices, or the chunk counts at which a slice ends, e.g. (8, 12, 16)
-        ends = {(k + 1) * C_ // int(S_) for k in range(max(1, min(int(S_), C_)))} if isinstance(S_, int) else {int(k) for k in S_}
-        ends.add(C_)
+        C_, ends = host_pipeline_plan(self.num_envs, host['obs'].numel() * host['obs'].element_size(), host.get('chunks'), host.get('forward_slices'))
         env.step_host_begin(host['actions'], host['obs'], host['reward'], host['done'], C_)
         f32 = host['obs'].dtype != torch.uint8
         if f32 and getattr(self, '_obs_f32', None) is None:
