@@ -293,6 +293,7 @@ constexpr int V2_ARR0 = 20 * 512, V2_ARR1 = 16 * 512;                  // bytes 
 constexpr int V2_PLANE = 3 * (V2_ARR0 + V2_ARR1);                       // 55,296: one of hi / lo
 constexpr int V2_OFF_B = 0, V2_OFF_A = B_BYTES, V2_OFF_XS = V2_OFF_A + 2 * V2_PLANE, V2_OFF_OUT = V2_OFF_XS + 2 * XS_BYTES,
               V2_OFF_BAR = V2_OFF_OUT + OUT_BYTES, V2_SMEM = V2_OFF_BAR + 256 + 1024;
+constexpr int V2_TMEM_COLS = 128;  // two accumulator buffers of 64 columns ([A W_hi sums | A_hi W_lo])
 constexpr int V2_C1_WARPS = 14, V2_THREADS = (5 + V2_C1_WARPS) * 32;    // 608: warp = (output row, column half)
 static_assert(V2_OFF_A % 1024 == 0 && V2_OFF_XS % 16 == 0 && V2_OFF_OUT % 16 == 0 && V2_OFF_BAR % 8 == 0 && V2_SMEM <= 227 * 1024, "layout");
 __host__ __device__ constexpr int v2_arr_base(int pr, int kj) { return pr == 0 ? kj * V2_ARR0 : 3 * V2_ARR0 + kj * V2_ARR1; }
@@ -319,14 +320,16 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc_fwd2_kernel(const XT *_
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == MMA_WARP) tmem_alloc(tmem_slot, TMEM_COLS);
+    if (warp == MMA_WARP) tmem_alloc(tmem_slot, V2_TMEM_COLS);
     for (int i = threadIdx.x; i < 32 * 144; i += V2_THREADS) {  // the weights: 9 K-major SWIZZLE_64B blocks, hi | lo (as version 1)
         const int oc = i / 144, rem = i - oc * 144, ic = rem / 9, tap = rem - ic * 9;
         float hi, lo;
         split1(w2[i], hi, lo);
-        const uint32_t off = (uint32_t)(tap * B_BLOCK) + kmajor_off(oc, ic >> 2) + (uint32_t)(ic & 3) * 4u;
+        // per tap: [hi block | lo block] = ONE 64-row operand (rows 0..31 = hi, 32..63 = lo), so that a single N = 64 MMA yields both
+        // A_hi W_hi and A_hi W_lo from one read of A_hi
+        const uint32_t off = (uint32_t)(2 * tap * B_BLOCK) + kmajor_off(oc, ic >> 2) + (uint32_t)(ic & 3) * 4u;
         *reinterpret_cast<float *>(sm + V2_OFF_B + off) = hi;
-        *reinterpret_cast<float *>(sm + V2_OFF_B + 9 * B_BLOCK + off) = lo;
+        *reinterpret_cast<float *>(sm + V2_OFF_B + B_BLOCK + off) = lo;
     }
     for (int i = threadIdx.x; i < (2 * V2_PLANE + 2 * XS_BYTES) / 4; i += V2_THREADS) reinterpret_cast<uint32_t *>(sm + V2_OFF_A)[i] = 0u;  // zero borders
     fence_proxy_async();
@@ -397,7 +400,10 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc_fwd2_kernel(const XT *_
 #undef T2D_PUT
         }
     } else if (warp == MMA_WARP) {
-        constexpr uint32_t idesc = idesc_tf32(128, 32, 0, 0);
+        // The kernel is bound by shared-memory bandwidth -- the tensor core's operand reads (4 KB of A per MMA at N = 32) plus the operand
+        // stores -- so the 3xTF32 products are issued as TWO MMAs per 8-deep step instead of three: A_hi [W_hi | W_lo] (N = 64, columns
+        // 0..31 and 32..63 of the accumulator) and A_lo W_hi (N = 32, columns 0..31); the epilogue adds the two halves.
+        constexpr uint32_t idesc32 = idesc_tf32(128, 32, 0, 0), idesc64 = idesc_tf32(128, 64, 0, 0);
         const uint64_t abase = umma_desc(0u, 128u, 512u, 0u);  // K-major, no swizzle: LBO = next 4 channels, SBO = next output position
         const uint64_t bbase = kmajor_desc(0u);
         int it = 0;
@@ -407,19 +413,18 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc_fwd2_kernel(const XT *_
             mbar_wait(bar_af, (uint32_t)it & 1u);
             tc_fence_after();
             if (elect_one()) {
-                const uint32_t d = tmem_base + (uint32_t)(abuf * 32);
+                const uint32_t d = tmem_base + (uint32_t)(abuf * 64);
 #pragma unroll
                 for (int tap = 0; tap < 9; ++tap) {
                     const int ki = tap / 3, kj = tap - 3 * ki;
                     const uint32_t a16 = (smem0 + V2_OFF_A + v2_arr_base(ki & 1, kj) + (ki >> 1) * 4 * 512) >> 4;
-                    const uint32_t b16 = (smem0 + V2_OFF_B + tap * B_BLOCK) >> 4;
+                    const uint32_t b16 = (smem0 + V2_OFF_B + 2 * tap * B_BLOCK) >> 4;
 #pragma unroll
                     for (int k8 = 0; k8 < 2; ++k8) {
                         const uint64_t a_hi = abase + (a16 + 16 * k8), a_lo = a_hi + (V2_PLANE >> 4);   // two channel quads = 256 bytes per MMA
-                        const uint64_t b_hi = bbase + (b16 + 2 * k8), b_lo = b_hi + ((9 * B_BLOCK) >> 4);
-                        tc_mma_tf32(d, a_lo, b_hi, idesc, (tap | k8) ? 1u : 0u);
-                        tc_mma_tf32(d, a_hi, b_lo, idesc, 1u);
-                        tc_mma_tf32(d, a_hi, b_hi, idesc, 1u);
+                        const uint64_t b_hi = bbase + (b16 + 2 * k8);
+                        tc_mma_tf32(d, a_hi, b_hi, idesc64, (tap | k8) ? 1u : 0u);
+                        tc_mma_tf32(d, a_lo, b_hi, idesc32, 1u);
                     }
                 }
                 tc_commit(bar_ae);                   // the operand arrays may be refilled
@@ -431,22 +436,21 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc_fwd2_kernel(const XT *_
         // ===== epilogue (identical to version 1) =====
         const int et = threadIdx.x;
         const int img = lane & 7, opos = warp * 4 + (lane >> 3);
-        float bias[32];
-#pragma unroll
-        for (int oc = 0; oc < 32; ++oc) bias[oc] = __ldg(b2 + oc);
         float *outs = reinterpret_cast<float *>(sm + V2_OFF_OUT);
         int it = 0;
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int abuf = it & 1;
             mbar_wait_backoff(bar_accf + 8 * abuf, (uint32_t)(it >> 1) & 1u);
             tc_fence_after();
-            uint32_t r[32];
-            tc_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(abuf * 32), r);
+            uint32_t r[32], r2[32];
+            tc_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(abuf * 64), r);
+            tc_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(abuf * 64 + 32), r2);
             tc_wait_ld();
             tc_fence_before();
             mbar_arrive(bar_acce + 8 * abuf);
 #pragma unroll
-            for (int oc = 0; oc < 32; ++oc) outs[img * OUT_IMG + oc * 16 + opos] = fmaxf(__uint_as_float(r[oc]) + bias[oc], 0.f);
+            for (int oc = 0; oc < 32; ++oc)
+                outs[img * OUT_IMG + oc * 16 + opos] = fmaxf(__uint_as_float(r[oc]) + __uint_as_float(r2[oc]) + __ldg(b2 + oc), 0.f);
             bar_sync(2, EPI_WARPS * 32);
             const long long n0 = tile * IMGS;
 #pragma unroll
@@ -462,7 +466,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc_fwd2_kernel(const XT *_
     __syncthreads();
     if (warp == MMA_WARP) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, TMEM_COLS);
+        tmem_dealloc(tmem_base, V2_TMEM_COLS);
     }
 }
 
