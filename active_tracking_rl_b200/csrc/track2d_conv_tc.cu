@@ -487,8 +487,8 @@ constexpr int BW2_BYTES = 4 * BW2_BLOCK;            // [hi | lo][2 reduction blo
 constexpr int BSTAGES = 2;
 constexpr int BA_SBO = 5 * 512;                     // COL^T: 144 rows = 4.5 atoms of 32 rows per group of 4 reduction indices
 constexpr int BA_PLANE = 4 * BA_SBO;                // 16 reduction indices
-constexpr int BB_SBO = 512;                         // dz2 as MN-major B: 32 rows = one atom per group
-constexpr int BB_PLANE = 4 * BB_SBO;
+constexpr int BB_SBO = 1024;                        // dz2 as MN-major B: per group of 4 reduction indices the hi atom (32 rows) and the lo atom side by
+constexpr int BB_PLANE = 4 * 512;                   // side = ONE 64-row operand [dz_hi | dz_lo] (see the dW2 MMAs); BB_PLANE = bytes of one of hi / lo
 constexpr int BSTAGE_BYTES = 2 * BA_PLANE + 2 * BB_PLANE;  // 24,576
 constexpr int DZA_BYTES = 4 * A_TILE;               // dz2 as the dCOL A operand: [hi | lo] x 2 reduction blocks of 128 x 16
 constexpr int DZT_PITCH = 36;                       // floats per row of the staged dz2 [m][oc]
@@ -512,7 +512,7 @@ constexpr int BOFF_XS = BOFF_DY + (DY_BYTES + 15) / 16 * 16;
 constexpr int BOFF_BAR = BOFF_XS + 2 * XS_BYTES;
 constexpr int BWD_SMEM = BOFF_BAR + 256 + 640 + 1024;  // barriers, conv1 weights + biases, alignment slack
 constexpr int BWD_THREADS = FWD_THREADS;
-constexpr int BTMEM_COLS = 512, TM_DW2 = 0, TM_DCOL = 64, TM_DCOL_STRIDE = 160;
+constexpr int BTMEM_COLS = 512, TM_DW2 = 0, TM_DCOL = 128, TM_DCOL_STRIDE = 160;  // dW2: 2 row blocks x [32 + 32] columns
 constexpr int PART_FLOATS = 32 * 144 + 144 + 16 + 32;  // per-CTA partial sums: dw2, dw1, db1, db2
 static_assert(BOFF_RING % 1024 == 0 && BOFF_DZA % 1024 == 0 && BSTAGE_BYTES % 512 == 0 && BOFF_DZT % 16 == 0 && BOFF_Y1 % 16 == 0, "shared-memory layout");
 static_assert(BWD_SMEM <= 227 * 1024, "shared memory");
@@ -658,7 +658,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) conv_tc_bwd_kernel(const XT *_
                     split4(lds128(smem0 + BOFF_DZT + (uint32_t)(m * DZT_PITCH + c8 * 4) * 4u), hi, lo);
                     const uint32_t off = 2 * BA_PLANE + mnmajor_off(kk, c8, BB_SBO);
                     sts128(st + off, hi);
-                    sts128(st + BB_PLANE + off, lo);
+                    sts128(st + off + 512, lo);
                 }
                 fence_proxy_async();
                 mbar_arrive(bar_full + 8 * s);
@@ -790,7 +790,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) conv_tc_bwd_kernel(const XT *_
         }
     } else if (warp == MMA_WARP) {
         // ===== MMA issuer =====
-        constexpr uint32_t idesc_col = idesc_tf32(128, 144, 0, 0), idesc_w = idesc_tf32(128, 32, 1, 1);
+        constexpr uint32_t idesc_col = idesc_tf32(128, 144, 0, 0), idesc_w = idesc_tf32(128, 32, 1, 1), idesc_w64 = idesc_tf32(128, 64, 1, 1);
         const uint64_t kbase = kmajor_desc(0u), abase = mnmajor_desc(0u, BA_SBO), bbase = mnmajor_desc(0u, BB_SBO);
         int ist = 0, it = 0;
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
@@ -824,14 +824,15 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) conv_tc_bwd_kernel(const XT *_
                     const uint32_t st16 = (smem0 + BOFF_RING + s * BSTAGE_BYTES) >> 4;
 #pragma unroll
                     for (int k8 = 0; k8 < 2; ++k8) {
-                        const uint64_t b_hi = bbase + (st16 + ((2 * BA_PLANE + k8 * 2 * BB_SBO) >> 4)), b_lo = b_hi + (BB_PLANE >> 4);
+                        // 3xTF32 in two MMAs: COL_hi^T [dz_hi | dz_lo] (N = 64: accumulator columns 0..31 and 32..63) and COL_lo^T dz_hi --
+                        // one operand read of COL_hi instead of two (the kernel lives on shared-memory bandwidth)
+                        const uint64_t b_hi = bbase + (st16 + ((2 * BA_PLANE + k8 * 2 * BB_SBO) >> 4));
 #pragma unroll
                         for (int half = 0; half < 2; ++half) {
                             const uint64_t a_hi = abase + (st16 + ((k8 * 2 * BA_SBO + half * 2048) >> 4)), a_lo = a_hi + (BA_PLANE >> 4);
-                            const uint32_t d = tmem_base + (uint32_t)(TM_DW2 + half * 32);
-                            tc_mma_tf32(d, a_lo, b_hi, idesc_w, (ist > 0 || k8 > 0) ? 1u : 0u);
-                            tc_mma_tf32(d, a_hi, b_lo, idesc_w, 1u);
-                            tc_mma_tf32(d, a_hi, b_hi, idesc_w, 1u);
+                            const uint32_t d = tmem_base + (uint32_t)(TM_DW2 + half * 64);
+                            tc_mma_tf32(d, a_hi, b_hi, idesc_w64, (ist > 0 || k8 > 0) ? 1u : 0u);
+                            tc_mma_tf32(d, a_lo, b_hi, idesc_w, 1u);
                         }
                     }
                     tc_commit(bar_empty + 8 * s);
@@ -874,23 +875,26 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) conv_tc_bwd_kernel(const XT *_
             mbar_arrive(bar_dyf);
         }
         __syncthreads();
-        // dW2^T [k_idx = (tap, ic)][oc]: rows 0..127 in columns 0..31, rows 128..143 in lanes 0..15 of columns 32..63
+        // dW2^T [k_idx = (tap, ic)][oc]: rows 0..127 in columns 0..31 (+ the COL_hi dz_lo part in 32..63), rows 128..143 in lanes 0..15 of
+        // columns 64..95 (+ 96..127)
         mbar_wait_backoff(bar_dw2, 0u);
         tc_fence_after();
-        uint32_t r[32];
+        uint32_t r[32], r2[32];
         tc_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)TM_DW2, r);
+        tc_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(TM_DW2 + 32), r2);
         tc_wait_ld();
         {
             const int kidx = warp * 32 + lane, tap = kidx >> 4, ic = kidx & 15;
 #pragma unroll
-            for (int oc = 0; oc < 32; ++oc) my_part[oc * 144 + ic * 9 + tap] = __uint_as_float(r[oc]);
+            for (int oc = 0; oc < 32; ++oc) my_part[oc * 144 + ic * 9 + tap] = __uint_as_float(r[oc]) + __uint_as_float(r2[oc]);
         }
         if (warp == 0) {
-            tc_ld32(tmem_base + (uint32_t)(TM_DW2 + 32), r);
+            tc_ld32(tmem_base + (uint32_t)(TM_DW2 + 64), r);
+            tc_ld32(tmem_base + (uint32_t)(TM_DW2 + 96), r2);
             tc_wait_ld();
             if (lane < 16) {
 #pragma unroll
-                for (int oc = 0; oc < 32; ++oc) my_part[oc * 144 + lane * 9 + 8] = __uint_as_float(r[oc]);
+                for (int oc = 0; oc < 32; ++oc) my_part[oc * 144 + lane * 9 + 8] = __uint_as_float(r[oc]) + __uint_as_float(r2[oc]);
             }
         }
     }
